@@ -1,0 +1,161 @@
+/*
+ * rpf_b200.h -- C ABI of the B200-native FFT worker for rtl_power_fftw.
+ *
+ * The reference has no plugin/FFI layer: its hot path is the body of
+ * Datastore::fftThread() (src/datastore.cxx:48-96) calling libfftw3f.  This
+ * header is the boundary a maintainer binds instead of <fftw3.h>: every entry
+ * point names the reference code it replaces (paths relative to the reference
+ * repository root).  Plain pointers and sizes only; no exceptions cross it;
+ * every function returns RPF_OK (0) or a negative rpf_status and leaves a
+ * message retrievable with rpf_strerror().
+ *
+ * Threading: a context is thread-compatible, not thread-safe -- one caller at
+ * a time, possibly a different thread per acquisition (the reference starts a
+ * fresh worker thread per hop, src/acquisition.cxx:256).  Every entry point
+ * selects the context's CUDA device itself.
+ *
+ * Index convention of pwr[]: identical to the reference's Datastore::pwr --
+ * pwr[i] is the summed |X|^2 of the bin at frequency (i - N/2) * fs / N
+ * (DC at i = N/2), consumed unchanged by Acquisition::write_data()
+ * (src/acquisition.cxx:377,391).
+ */
+#ifndef RPF_B200_H
+#define RPF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPF_B200_ABI_VERSION 1
+
+typedef enum rpf_status {
+    RPF_OK = 0,
+    RPF_ERR_INVALID_ARG = -1,   /* NULL pointer, odd byte count, N odd or < 2 ...            */
+    RPF_ERR_UNSUPPORTED_N = -2, /* N is valid for the reference but not implemented on GPU   */
+    RPF_ERR_CUDA = -3,          /* a CUDA runtime call or kernel failed (message has detail) */
+    RPF_ERR_NOMEM = -4,
+    RPF_ERR_STATE = -5          /* call sequence error                                       */
+} rpf_status;
+
+typedef struct rpf_ctx rpf_ctx;
+
+/* Mirrors the Params fields the hot path reads (src/params.h:33,42-43,52) plus
+ * placement.  Zero-initialise, then set what you need. */
+typedef struct rpf_config {
+    int32_t      N;             /* Params::N: number of bins; even (src/params.cxx:152-155)  */
+    int32_t      device;        /* CUDA device ordinal                                       */
+    const float *window;        /* NULL, or N window values (copied): AuxData::window_values,
+                                   applied as in src/datastore.cxx:76-77                     */
+    int64_t      buf_length;    /* Params::buf_length: typical bytes per push (sizing hint)  */
+    uint32_t     flags;         /* RPF_FLAG_*                                                */
+    int32_t      reserved[5];
+} rpf_config;
+
+#define RPF_FLAG_NONE 0u
+
+/* Plays the role of fftwf_alloc_complex x2 + fftwf_plan_dft_1d(N, in, out,
+ * FFTW_FORWARD, FFTW_MEASURE) in Datastore::Datastore (src/datastore.cxx:30-33):
+ * builds twiddle tables, allocates device staging and accumulators.
+ * The context starts reset with repeats = INT64_MAX. */
+int rpf_create(const rpf_config *cfg, rpf_ctx **out);
+
+/* fftwf_destroy_plan + fftwf_free x2 in Datastore::~Datastore
+ * (src/datastore.cxx:43-45).  NULL is allowed. */
+void rpf_destroy(rpf_ctx *ctx);
+
+/* Start of one Acquisition::run(): std::fill(pwr, 0), repeats_done = 0
+ * (src/acquisition.cxx:252-254) and the fresh worker's fft_pointer = 0
+ * (src/datastore.cxx:52).  `repeats` is Params::repeats (src/params.h:55):
+ * the worker stops after that many spectra (src/datastore.cxx:67). */
+int rpf_reset(rpf_ctx *ctx, int64_t repeats);
+
+/* The worker body for one Buffer (src/datastore.cxx:66-89): consume `len`
+ * bytes (interleaved I,Q uint8, bias 127) of the continuous sample stream.
+ * Spectrum boundaries are independent of buffer boundaries (fft_pointer
+ * persists, src/datastore.cxx:52,68,81,87); bytes arriving after `repeats`
+ * spectra are discarded (src/datastore.cxx:67); a trailing partial spectrum is
+ * kept for the next push.  `len` must be even (the reference reads
+ * buffer[p+1] unconditionally, src/datastore.cxx:74).
+ * On return `bytes` may be reused (the host->device copy has completed); the
+ * FFT work itself continues asynchronously on the context's stream. */
+int rpf_push(rpf_ctx *ctx, const uint8_t *bytes, size_t len);
+
+/* Same, for a buffer already resident in this context's device memory (the
+ * HBM-resident benchmark path).  Enqueued on the context's stream; `bytes`
+ * must stay valid until rpf_sync()/rpf_finish().  Zero-copy when no partial
+ * spectrum is pending and `bytes` is 16-byte aligned. */
+int rpf_push_device(rpf_ctx *ctx, const uint8_t *bytes, size_t len);
+
+/* Wait for everything enqueued so far. */
+int rpf_sync(rpf_ctx *ctx);
+
+/* What the producer thread reads after t.join() (src/acquisition.cxx:347,
+ * 352-357,377-398): pwr_out[N] = Datastore::pwr (summed, not averaged,
+ * float64), *repeats_done = Datastore::repeats_done.  Either may be NULL.
+ * Does not reset; may be called repeatedly. */
+int rpf_finish(rpf_ctx *ctx, double *pwr_out, int64_t *repeats_done);
+
+/* As rpf_finish but pwr_out_device is device memory (N doubles) and the call
+ * only enqueues work on the context's stream -- used before a cross-GPU
+ * allreduce of pwr[] (the caller's collective runs on the same stream). */
+int rpf_finish_device(rpf_ctx *ctx, double *pwr_out_device, int64_t *repeats_done);
+
+/* Datastore::repeats_done (src/datastore.h:38) without synchronising. */
+int64_t rpf_repeats_done(const rpf_ctx *ctx);
+
+/* Number of complex samples of a partial spectrum currently held
+ * (the reference's local fft_pointer, src/datastore.cxx:52). */
+int64_t rpf_fft_pointer(const rpf_ctx *ctx);
+
+/* Run the context on a caller-owned CUDA stream (a cudaStream_t passed as
+ * void*; NULL restores the context's own stream).  Synchronises first. */
+int rpf_set_stream(rpf_ctx *ctx, void *cuda_stream);
+
+/* Message for the last error on this context (or for create failures when
+ * ctx is NULL).  Never NULL. */
+const char *rpf_strerror(const rpf_ctx *ctx);
+
+/* Number of this library's kernel launches issued by the context so far. */
+int64_t rpf_kernel_launches(const rpf_ctx *ctx);
+
+/* Name of the kernel family selected for this N ("small", "fused3", "fourstep"). */
+const char *rpf_plan_name(const rpf_ctx *ctx);
+
+/* ---- Acquisition::write_data() arithmetic on the device ------------------
+ * (src/acquisition.cxx:377,390-399): DC-bin interpolation, /repeats_done/N/fs,
+ * 10*log10 unless linear, baseline subtraction.  Leaves the context's pwr
+ * untouched (works on a copy, as write_data mutates pwr only for output).
+ * freq_out / val_out: host arrays of N doubles (freq_out may be NULL);
+ * baseline: NULL or N host doubles. */
+int rpf_write_data(rpf_ctx *ctx, double tuned_freq, int32_t actual_samplerate, int32_t linear,
+                   const double *baseline, double *freq_out, double *val_out);
+
+/* ---- synthetic IQ source (stands in for Rtlsdr::read, src/device.cxx:92-97) --
+ * Counter-based generator, bit-identical on host and device (integer
+ * arithmetic only): byte i of the stream depends only on (seed, mode, i).
+ *   mode 0: uniform on [0,255]
+ *   mode 1: clipped Gaussian, mean 127.4, sigma 30  (a dongle with AGC)
+ *   mode 2: tone at +fs/8 (bin N/2 + N/8 for any N divisible by 8), amplitude
+ *           100, plus Gaussian noise sigma 5        (exercises bin indexing)
+ * `stream_offset` is the absolute byte offset of bytes[0] in the stream. */
+void rpf_synth_fill_host(uint8_t *bytes, size_t len, uint64_t stream_offset, uint64_t seed,
+                         int32_t mode);
+int rpf_synth_fill_device(uint8_t *bytes_device, size_t len, uint64_t stream_offset, uint64_t seed,
+                          int32_t mode, int32_t device, void *cuda_stream);
+
+/* Pinned host memory helpers so the caller's Buffers can be DMA targets
+ * (Datastore's Buffer pool, src/datastore.cxx:27-28). */
+int rpf_host_alloc(void **out, size_t bytes);
+void rpf_host_free(void *p);
+int rpf_host_register(void *p, size_t bytes);
+int rpf_host_unregister(void *p);
+
+int rpf_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPF_B200_H */

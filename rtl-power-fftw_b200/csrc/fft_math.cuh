@@ -1,0 +1,151 @@
+// fft_math.cuh -- in-register radix-2/4/8/16 DFT butterflies on packed FP32.
+//
+// One complex value = one 64-bit register pair (float2: x = re, y = im).
+// sm_100a executes FADD2/FMUL2/FFMA2 on such pairs in a single issue slot, and
+// (verified in SASS) takes a free half-swap (.LO_HI), a free per-half negate
+// (.NP) and a free scalar broadcast (Rn.F32 / immediate) on its operands.  So
+//   complex add/sub            = 1 FADD2
+//   multiply by -i / +i        = folded into the consumer's operand modifiers
+//   complex * (wr + i wi)      = FMUL2 + FFMA2 with *scalar* twiddle registers
+// and a radix-4 butterfly is 8 issue slots, a radix-16 is 80.
+//
+// Forward transform, exponent sign -1, unnormalised: the contract of
+// fftwf_plan_dft_1d(..., FFTW_FORWARD, ...) at reference src/datastore.cxx:32-33.
+#pragma once
+#include <cuda_runtime.h>
+
+typedef float2 c32;
+
+__device__ __forceinline__ c32 cadd(c32 a, c32 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ c32 csub(c32 a, c32 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a + (-i) b  and  a + (+i) b
+__device__ __forceinline__ c32 cadd_mi(c32 a, c32 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }
+__device__ __forceinline__ c32 cadd_pi(c32 a, c32 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }
+// (ar + i ai)(wr + i wi) = (ar wr - ai wi) + i (ai wr + ar wi)
+__device__ __forceinline__ c32 cmul(c32 a, float wr, float wi)
+{
+    const c32 t = __fmul2_rn(a, make_float2(wr, wr));
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(-wi, wi), t);
+}
+__device__ __forceinline__ c32 cmul(c32 a, c32 w) { return cmul(a, w.x, w.y); }
+
+// cos(2 pi j / 16), j = 0..15, as compile-time constants.
+__host__ __device__ constexpr float rpf_cos16(int j)
+{
+    return j == 0 ? 1.0f
+         : j == 1 ? 0.923879532511286756f
+         : j == 2 ? 0.707106781186547524f
+         : j == 3 ? 0.382683432365089772f
+         : j == 4 ? 0.0f
+         : j == 5 ? -0.382683432365089772f
+         : j == 6 ? -0.707106781186547524f
+         : j == 7 ? -0.923879532511286756f
+         : j == 8 ? -1.0f
+         : j == 9 ? -0.923879532511286756f
+         : j == 10 ? -0.707106781186547524f
+         : j == 11 ? -0.382683432365089772f
+         : j == 12 ? 0.0f
+         : j == 13 ? 0.382683432365089772f
+         : j == 14 ? 0.707106781186547524f
+         : 0.923879532511286756f;
+}
+// multiply by W_16^J = exp(-2 pi i J / 16), J a compile-time constant
+template <int J>
+__device__ __forceinline__ c32 mul_w16(c32 a)
+{
+    constexpr int j = ((J % 16) + 16) % 16;
+    if (j == 0) return a;
+    if (j == 4) return make_float2(a.y, -a.x);     // -i
+    if (j == 8) return make_float2(-a.x, -a.y);    // -1
+    if (j == 12) return make_float2(-a.y, a.x);    // +i
+    // wr = cos(2 pi j/16), wi = -sin(2 pi j/16) = -cos(2 pi (j-4)/16)
+    return cmul(a, rpf_cos16(j), -rpf_cos16((j + 12) % 16));
+}
+
+template <int R> struct Dft;
+
+template <> struct Dft<1> {
+    static __device__ __forceinline__ void run(c32 *) {}
+};
+template <> struct Dft<2> {
+    static __device__ __forceinline__ void run(c32 *x)
+    {
+        const c32 a = x[0], b = x[1];
+        x[0] = cadd(a, b);
+        x[1] = csub(a, b);
+    }
+};
+template <> struct Dft<4> {
+    static __device__ __forceinline__ void run(c32 *x)
+    {
+        const c32 s0 = cadd(x[0], x[2]), s1 = csub(x[0], x[2]);
+        const c32 s2 = cadd(x[1], x[3]), s3 = csub(x[1], x[3]);
+        x[0] = cadd(s0, s2);
+        x[1] = cadd_mi(s1, s3);
+        x[2] = csub(s0, s2);
+        x[3] = cadd_pi(s1, s3);
+    }
+};
+
+// Cooley-Tukey inside a thread: R = R1*R2, n = R2*n1 + n0, k = k0 + R1*k1.
+//   A[n0][k0] = DFT_R1 over n1;  A *= W_R^{n0 k0};  X[k0 + R1 k1] = DFT_R2 over n0.
+template <int R1, int R2>
+__device__ __forceinline__ void dft_composite(c32 *x)
+{
+    constexpr int R = R1 * R2;
+    constexpr int S = 16 / R;   // W_R^j = W_16^{S j}
+    c32 a[R2][R1];
+#pragma unroll
+    for (int n0 = 0; n0 < R2; n0++) {
+        c32 col[R1];
+#pragma unroll
+        for (int n1 = 0; n1 < R1; n1++) col[n1] = x[R2 * n1 + n0];
+        Dft<R1>::run(col);
+#pragma unroll
+        for (int k0 = 0; k0 < R1; k0++) a[n0][k0] = col[k0];
+    }
+    // twiddles: n0*k0 products are compile-time after full unrolling; the
+    // switch collapses to one case per (n0,k0).
+#pragma unroll
+    for (int n0 = 1; n0 < R2; n0++) {
+#pragma unroll
+        for (int k0 = 1; k0 < R1; k0++) {
+            const int j = (S * n0 * k0) % 16;
+            c32 v = a[n0][k0];
+            switch (j) {
+                case 0: break;
+                case 1: v = mul_w16<1>(v); break;
+                case 2: v = mul_w16<2>(v); break;
+                case 3: v = mul_w16<3>(v); break;
+                case 4: v = mul_w16<4>(v); break;
+                case 5: v = mul_w16<5>(v); break;
+                case 6: v = mul_w16<6>(v); break;
+                case 7: v = mul_w16<7>(v); break;
+                case 8: v = mul_w16<8>(v); break;
+                case 9: v = mul_w16<9>(v); break;
+                case 10: v = mul_w16<10>(v); break;
+                case 11: v = mul_w16<11>(v); break;
+                case 12: v = mul_w16<12>(v); break;
+                case 13: v = mul_w16<13>(v); break;
+                case 14: v = mul_w16<14>(v); break;
+                default: v = mul_w16<15>(v); break;
+            }
+            a[n0][k0] = v;
+        }
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < R1; k0++) {
+        c32 row[R2];
+#pragma unroll
+        for (int n0 = 0; n0 < R2; n0++) row[n0] = a[n0][k0];
+        Dft<R2>::run(row);
+#pragma unroll
+        for (int k1 = 0; k1 < R2; k1++) x[k0 + R1 * k1] = row[k1];
+    }
+}
+template <> struct Dft<8> {
+    static __device__ __forceinline__ void run(c32 *x) { dft_composite<2, 4>(x); }
+};
+template <> struct Dft<16> {
+    static __device__ __forceinline__ void run(c32 *x) { dft_composite<4, 4>(x); }
+};

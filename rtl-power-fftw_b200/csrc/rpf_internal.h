@@ -1,0 +1,40 @@
+// rpf_internal.h -- launch interfaces between rpf_capi.cu and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// Source of one launch of the fused kernels.
+struct RpfLaunch {
+    const uint8_t *bytes;     // SRC_U8: 16-byte aligned start of spectrum 0 (2N bytes per spectrum)
+    const float2  *cplx;      // SRC_C32: four-step scratch, [spec][k1][n] complex64
+    int64_t        nspec;     // spectra (SRC_U8) / spectra in the batch S (SRC_C32)
+    int            M;         // four-step outer radix (1 for the direct path)
+    const float2  *twiddle;   // W_N^j, j in [0,N): (cos, -sin)
+    const float   *window;    // N floats or nullptr
+    double        *rows;      // private accumulator rows [grid*G][N*M]
+    int            grid;
+    cudaStream_t   stream;
+};
+
+// Fused unpack -> (window) -> N-point FFT -> |X|^2 accumulate, N in {512,1024,2048,4096}.
+cudaError_t rpf_launch_fused3(int N, const RpfLaunch &L);
+int rpf_fused3_groups(int N);          // spectra per CTA iteration (G)
+bool rpf_fused3_supported(int N);
+cudaError_t rpf_fused3_configure();    // opt-in shared memory attributes (once per device)
+
+// Generic power-of-two N in [2,256]: shared-memory radix-2 Stockham.
+cudaError_t rpf_launch_small(int N, const RpfLaunch &L);
+
+// Four-step outer pass for N = M*4096: radix-M over the stride-4096 digit + twiddle.
+cudaError_t rpf_launch_fourstep_outer(int M, const uint8_t *bytes, int64_t nspec, const float2 *twiddle_big,
+                                      const float *window, float2 *scratch, cudaStream_t stream);
+
+// pwr[i] = sum over rows (fixed order, float64).
+cudaError_t rpf_launch_reduce_rows(const double *rows, int nrows, int64_t rowlen, double *pwr, cudaStream_t stream);
+
+cudaError_t rpf_launch_synth(uint8_t *bytes, size_t len, uint64_t stream_offset, uint64_t seed, int mode,
+                             cudaStream_t stream);
+
+cudaError_t rpf_launch_write_data(const double *pwr, int N, int64_t repeats_done, double tuned_freq,
+                                  int samplerate, int linear, const double *baseline, double *freq_out,
+                                  double *val_out, cudaStream_t stream);

@@ -1,0 +1,117 @@
+#include "acquisition.h"
+
+#include <cmath>
+#include <iomanip>
+#include <iostream>
+#include <thread>
+
+bool SyntheticSource::read(Buffer &buffer)
+{
+    rpf_synth_fill_host(buffer.data(), buffer.size(), offset, seed, mode);
+    offset += buffer.size();
+    return true;
+}
+
+Plan::Plan(Params &p, int rate) : actual_samplerate(rate), params(p)
+{
+    // buffer auto-sizing rule of src/acquisition.cxx:166-176
+    if (!params.buf_length_isSet) {
+        int64_t mult = (int64_t)std::ceil((2.0 * params.N * params.repeats) / base_buf);
+        if (mult <= default_buf_multiplier) params.buf_length = base_buf * (mult == 0 ? 1 : mult);
+    }
+}
+
+Acquisition::Acquisition(const Params &p, AuxData &a, SampleSource &s, Datastore &d, int rate, int64_t f)
+    : params(p), aux(a), source(s), data(d), actual_samplerate(rate), freq(f) {}
+
+void Acquisition::run()
+{
+    source.set_frequency(freq);
+    tuned_freq = source.frequency();
+
+    // src/acquisition.cxx:252-256: reset, then one worker thread per acquisition
+    std::fill(data.pwr.begin(), data.pwr.end(), 0);
+    data.acquisition_finished = false;
+    data.repeats_done = 0;
+    std::thread worker(&Datastore::fftThread, &data);
+
+    // producer loop, src/acquisition.cxx:271-332
+    std::unique_lock<std::mutex> lock(data.status_mutex, std::defer_lock);
+    const int64_t dataTotal = 2 * (int64_t)params.N * params.repeats;
+    int64_t dataRead = 0;
+    while (dataRead < dataTotal) {
+        lock.lock();
+        data.queue_histogram[data.empty_buffers.size()]++;       // back-pressure gauge
+        data.status_change.wait(lock, [this] { return !data.empty_buffers.empty(); });
+        Buffer &buffer = *data.empty_buffers.front();
+        data.empty_buffers.pop_front();
+        lock.unlock();
+
+        int64_t dataNeeded = dataTotal - dataRead;
+        if (dataNeeded >= params.buf_length) {
+            dataNeeded = params.buf_length;
+        } else {   // last read: round up to the USB quantum, capped at one buffer
+            dataNeeded = base_buf * (int64_t)std::ceil((double)dataNeeded / base_buf);
+            if (dataNeeded > params.buf_length) dataNeeded = params.buf_length;
+        }
+        buffer.resize(dataNeeded);
+
+        const bool ok = source.read(buffer);
+        deviceReadouts++;
+        lock.lock();
+        if (!ok) {
+            std::cerr << "Error: dropped samples." << std::endl;
+            data.empty_buffers.push_front(&buffer);               // retry with the same buffer
+        } else {
+            successfulReadouts++;
+            dataRead += dataNeeded;
+            data.occupied_buffers.push_back(&buffer);
+            data.status_change.notify_all();
+        }
+        lock.unlock();
+    }
+    lock.lock();
+    data.acquisition_finished = true;
+    data.status_change.notify_all();
+    lock.unlock();
+    worker.join();
+    data.rethrow_worker_error();   // CUDA failure -> RPFexception(HardwareError) on this thread
+}
+
+void Acquisition::print_summary() const
+{
+    std::cerr << "Actual number of (complex) samples collected: " << (int64_t)params.N * data.repeats_done << std::endl;
+    std::cerr << "Actual number of device readouts: " << deviceReadouts << std::endl;
+    std::cerr << "Number of successful readouts: " << successfulReadouts << std::endl;
+    std::cerr << "Actual number of averaged spectra: " << data.repeats_done << std::endl;
+    std::cerr << "Effective integration time: " << (double)params.N * data.repeats_done / actual_samplerate
+              << " seconds" << std::endl;
+}
+
+// Text output of src/acquisition.cxx:360-433 (non-matrix mode, without the
+// timestamp header lines).  The arithmetic (DC interpolation, normalisation,
+// dB, baseline) runs on the device: rpf_write_data().
+void Acquisition::write_data(std::ostream &out) const
+{
+    const int N = params.N;
+    std::vector<double> f(N), v(N);
+    int rc = rpf_write_data(data.context(), (double)tuned_freq, actual_samplerate, params.linear ? 1 : 0,
+                            params.baseline ? aux.baseline_values.data() : nullptr, f.data(), v.data());
+    if (rc != RPF_OK)
+        throw RPFexception(std::string("write_data: ") + rpf_strerror(data.context()), ReturnValue::HardwareError);
+    // the reference mutates pwr[N/2] while printing (src/acquisition.cxx:377); keep that visible
+    data.pwr[N / 2] = (data.pwr[N / 2 - 1] + data.pwr[N / 2 + 1]) / 2;
+
+    out << "# rtl-power-fftw output" << std::endl;
+    out << "#" << std::endl;
+    out << "# frequency [Hz] power spectral density [dB/Hz]" << std::endl;
+    const int extraDigitsFreq = 2;
+    const int significantPlacesFreq =
+        (int)std::ceil(std::floor(std::log10((double)tuned_freq)) - std::log10((double)actual_samplerate / N) + 1 + extraDigitsFreq);
+    const int significantPlacesPwr = 6;
+    for (int i = 0; i < N; i++)
+        out << std::setprecision(significantPlacesFreq) << f[i] << " " << std::setprecision(significantPlacesPwr)
+            << v[i] << std::endl;
+    out << std::endl;
+    out.flush();
+}

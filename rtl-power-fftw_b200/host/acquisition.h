@@ -1,0 +1,67 @@
+// acquisition.h -- the callers either side of the hot path, reference-shaped:
+//   SampleSource  : what Acquisition needs of Rtlsdr (src/device.h:28-54):
+//                   read(Buffer&), set_frequency(), frequency()
+//   SyntheticSource: counter-based IQ bytes (rpf_synth_fill_host) instead of USB
+//   AuxData       : window / baseline values (src/acquisition.h:33-41)
+//   Plan          : repeats / buffer auto-sizing (src/acquisition.cxx:158-176; no hopping)
+//   Acquisition   : run() / print_summary() / write_data() (src/acquisition.h:81-98)
+#pragma once
+#include <cstdint>
+#include <iosfwd>
+#include <string>
+#include <vector>
+
+#include "datastore.h"
+
+class SampleSource {
+  public:
+    virtual ~SampleSource() {}
+    virtual bool read(Buffer &buffer) = 0;            // Rtlsdr::read (src/device.cxx:92-97)
+    virtual void set_frequency(int64_t f) { freq = f; }
+    virtual int64_t frequency() const { return freq; }
+  protected:
+    int64_t freq = 0;
+};
+
+class SyntheticSource : public SampleSource {
+  public:
+    SyntheticSource(uint64_t seed, int mode) : seed(seed), mode(mode) {}
+    bool read(Buffer &buffer) override;
+    void rewind() { offset = 0; }
+    uint64_t offset = 0;
+  private:
+    uint64_t seed;
+    int mode;
+};
+
+struct AuxData {
+    std::vector<double> baseline_values;
+    std::vector<float> window_values;
+};
+
+class Plan {
+  public:
+    Plan(Params &params, int actual_samplerate);
+    int actual_samplerate;
+  protected:
+    Params &params;
+};
+
+class Acquisition {
+  public:
+    Acquisition(const Params &params, AuxData &aux, SampleSource &source, Datastore &data,
+                int actual_samplerate, int64_t freq);
+    void run();
+    void print_summary() const;
+    void write_data(std::ostream &out) const;
+
+    int64_t deviceReadouts = 0, successfulReadouts = 0;
+  protected:
+    const Params &params;
+    AuxData &aux;
+    SampleSource &source;
+    Datastore &data;
+    int actual_samplerate;
+    int64_t freq;
+    int64_t tuned_freq = 0;
+};

@@ -1,0 +1,251 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/rpf_b200.h),
+against the CPU oracle on identical bytes.
+
+Tolerance (BASELINE.json north_star): 1e-5 relative, float32 path vs the
+float64 oracle; bin indices exact.  For noise-like input the bound is applied
+per bin; for tonal input relative to the largest bin."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from rpf import Context, RpfError, pkg
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def stream(nbytes, seed=1, mode=0):
+    return pkg.synth_fill_host(nbytes, 0, seed=seed, mode=mode)
+
+
+def run_gpu(N, repeats, chunks, window=None):
+    with Context(N, window=window) as c:
+        c.reset(repeats)
+        for ch in chunks:
+            c.push(ch)
+        return c.finish()
+
+
+def perbin(a, b):
+    return np.max(np.abs(a - b) / b)
+
+
+def relmax(a, b):
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+@pytest.mark.parametrize("N", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536])
+def test_random_bytes_all_sizes(N):
+    R = max(3, min(40, (1 << 19) // N))
+    s = stream(2 * N * R, seed=N)
+    pg, done = run_gpu(N, R, [s])
+    po, done_o = ol.oracle_run_stream(N, R, s, buf_length=s.size)
+    assert done == done_o == R
+    assert perbin(pg, po) < TOL
+    assert np.argmax(pg) == np.argmax(po)
+
+
+@pytest.mark.parametrize("N", [8, 512, 4096, 65536])
+def test_kat_zero_dc_nyquist_tone(N):
+    z = np.full(2 * N * 2, 127, np.uint8)
+    p, done = run_gpu(N, 2, [z])
+    assert done == 2 and np.all(p == 0.0)                      # exact
+    a = 40
+    d = z[: 2 * N].copy()
+    d[0::2] = 127 + a
+    p, _ = run_gpu(N, 1, [d])
+    assert np.argmax(p) == N // 2
+    assert p[N // 2] == pytest.approx((a * N) ** 2, rel=1e-6)
+    assert np.max(np.delete(p, N // 2)) <= 1e-9 * p[N // 2]
+    n = np.arange(N)
+    q = z[: 2 * N].copy()
+    q[0::2] = 127 + 50 * (1 - 2 * (n % 2))
+    p, _ = run_gpu(N, 1, [q])
+    assert np.argmax(p) == 0
+    k, A = N // 8 + 1, 100.0
+    t = np.empty(2 * N, np.uint8)
+    t[0::2] = np.round(127 + A * np.cos(2 * np.pi * k * n / N))
+    t[1::2] = np.round(127 + A * np.sin(2 * np.pi * k * n / N))
+    p, _ = run_gpu(N, 1, [t])
+    po, _ = ol.oracle_run_stream(N, 1, t, buf_length=t.size)
+    assert np.argmax(p) == N // 2 + k
+    assert relmax(p, po) < TOL
+
+
+@pytest.mark.parametrize("N", [16, 512, 4096, 16384])
+def test_parseval(N):
+    R = 6
+    s = stream(2 * N * R, seed=7 + N)
+    p, _ = run_gpu(N, R, [s])
+    x = s.astype(np.int64) - 127
+    assert p.sum() == pytest.approx(N * float((x * x).sum()), rel=1e-6)
+
+
+@pytest.mark.parametrize("N,mode", [(512, 1), (4096, 1), (4096, 2), (65536, 2)])
+def test_gaussian_and_tone_modes(N, mode):
+    R = 12 if N < 65536 else 3
+    s = stream(2 * N * R, seed=3, mode=mode)
+    pg, _ = run_gpu(N, R, [s])
+    po, _ = ol.oracle_run_stream(N, R, s, buf_length=s.size)
+    assert relmax(pg, po) < TOL
+    if mode == 1:
+        assert perbin(pg, po) < TOL
+    else:
+        assert np.argmax(pg) == N // 2 + N // 8 == np.argmax(po)
+
+
+@pytest.mark.parametrize("N", [512, 4096, 65536])
+def test_window_hann(N):
+    R = 5
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32)
+    s = stream(2 * N * R, seed=11)
+    pg, _ = run_gpu(N, R, [s], window=w)
+    po, _ = ol.oracle_run_stream(N, R, s, window=w, buf_length=s.size)
+    assert relmax(pg, po) < TOL
+    assert np.max(np.abs(pg - po) / po) < 1e-4      # per bin, incl. the deep skirts of the DC line
+
+
+def test_config1_reference_shape():
+    """BASELINE config 1: 512 bins, 100 spectra, one 114,688-byte read, 12 surplus spectra."""
+    N, R = 512, 100
+    s = stream(114688, seed=0x5EED + 1)
+    pg, done = run_gpu(N, R, [s])
+    po, _ = ol.oracle_run_stream(N, R, s, buf_length=114688)
+    assert done == 100 and perbin(pg, po) < TOL
+    s2 = s.copy()
+    s2[2 * N * R:] = 0
+    pg2, _ = run_gpu(N, R, [s2])
+    assert np.array_equal(pg, pg2)                   # bytes past 2*N*repeats have no effect
+
+
+@pytest.mark.parametrize("N,chunk", [(65536, 1638400), (4096, 16384 * 5 + 2), (512, 1000), (64, 6), (65536, 4096)])
+def test_straddling_buffers_equal_contiguous(N, chunk):
+    """Spectrum boundaries are independent of buffer boundaries (src/datastore.cxx:52,68)."""
+    R = 5 if N == 65536 else 37
+    s = stream(2 * N * R + 2 * (N // 2), seed=5)     # ends with half a spectrum
+    chunks = [s[i:i + chunk] for i in range(0, s.size, chunk)]
+    with Context(N) as c:
+        c.reset(10 ** 9)
+        for ch in chunks:
+            c.push(ch)
+        pg, done = c.finish()
+        assert done == R and c.fft_pointer == N // 2
+    po, _ = ol.oracle_run_stream(N, R, s, buf_length=s.size)
+    assert perbin(pg, po) < TOL
+
+
+def test_repeats_limit_and_reset():
+    N = 4096
+    s = stream(2 * N * 20, seed=2)
+    with Context(N) as c:
+        c.reset(7)
+        c.push(s[: 2 * N * 5 + 100])
+        assert c.repeats_done == 5
+        c.push(s[2 * N * 5 + 100:])
+        assert c.repeats_done == 7 and c.fft_pointer == 0
+        c.push(s)                                     # discarded
+        p7, done = c.finish()
+        assert done == 7
+        po, _ = ol.oracle_run_stream(N, 7, s, buf_length=s.size)
+        assert perbin(p7, po) < TOL
+        c.reset(3)
+        p0, d0 = c.finish()
+        assert d0 == 0 and np.all(p0 == 0)
+        c.push(s)
+        p3, d3 = c.finish()
+        po3, _ = ol.oracle_run_stream(N, 3, s, buf_length=s.size)
+        assert d3 == 3 and perbin(p3, po3) < TOL
+
+
+def test_argument_errors():
+    with pytest.raises(RpfError) as e:
+        Context(511)
+    assert e.value.code == -1
+    with pytest.raises(RpfError) as e:
+        Context(500)
+    assert e.value.code == -2                         # valid for the reference, unsupported on GPU: loud
+    with Context(64) as c:
+        with pytest.raises(RpfError):
+            c.push(np.zeros(3, np.uint8))
+        with pytest.raises(RpfError):
+            c.reset(-1)
+
+
+def test_device_source_and_generator_identity():
+    import torch
+    N, R = 4096, 64
+    nbytes = 2 * N * R
+    dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    for mode in (0, 1, 2):
+        pkg.synth_fill_device(dev.data_ptr(), nbytes, 0, seed=77, mode=mode)
+        torch.cuda.synchronize()
+        host = pkg.synth_fill_host(nbytes, 0, seed=77, mode=mode)
+        assert np.array_equal(dev.cpu().numpy(), host)
+    # unaligned offset / odd length
+    pkg.synth_fill_device(dev.data_ptr() + 3, 1001, 12345, seed=9, mode=1)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy()[3:1004], pkg.synth_fill_host(1001, 12345, seed=9, mode=1))
+    pkg.synth_fill_device(dev.data_ptr(), nbytes, 0, seed=77, mode=0)
+    torch.cuda.synchronize()
+    host = pkg.synth_fill_host(nbytes, 0, seed=77, mode=0)
+    with Context(N) as c:
+        c.reset(R)
+        c.push_device(dev.data_ptr(), nbytes)         # zero-copy path
+        pd, done = c.finish()
+        assert done == R
+        c.reset(R)
+        c.push_device(dev.data_ptr(), 2 * N * 3 + 10)  # leaves a carry -> staged path next
+        c.push_device(dev.data_ptr() + 2 * N * 3 + 10, nbytes - (2 * N * 3 + 10))
+        pd2, done2 = c.finish()
+    po, _ = ol.oracle_run_stream(N, R, host, buf_length=nbytes)
+    assert done2 == R and perbin(pd, po) < TOL and perbin(pd2, po) < TOL
+
+
+def test_linearity_large_config2_shape():
+    """Config 2 shape (4096 bins, 1e6 spectra) via a periodic device-resident ring:
+    pwr(R*P spectra) == R * pwr(P spectra) (SURVEY section 4 'linearity in repeats')."""
+    import torch
+    N, P, reps = 4096, 1000, 1000                    # 1e6 spectra
+    nbytes = 2 * N * P
+    dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    pkg.synth_fill_device(dev.data_ptr(), nbytes, 0, seed=0x5EED + 2, mode=1)
+    torch.cuda.synchronize()
+    with Context(N) as c:
+        c.reset(P)
+        c.push_device(dev.data_ptr(), nbytes)
+        p1, d1 = c.finish()
+        c.reset(P * reps)
+        for _ in range(reps):
+            c.push_device(dev.data_ptr(), nbytes)
+        pr, dr = c.finish()
+    assert d1 == P and dr == P * reps
+    assert np.max(np.abs(pr - reps * p1) / (reps * p1)) < 1e-9   # float64 second level
+    host = pkg.synth_fill_host(2 * N * 50, 0, seed=0x5EED + 2, mode=1)
+    po, _ = ol.oracle_run_stream(N, 50, host, buf_length=host.size)
+    with Context(N) as c:
+        c.reset(50)
+        c.push(host)
+        p50, _ = c.finish()
+    assert perbin(p50, po) < TOL
+
+
+def test_write_data_matches_oracle():
+    import ctypes as C
+    N, R = 4096, 9
+    s = stream(2 * N * R, seed=21)
+    base = np.linspace(-1, 1, N)
+    with Context(N) as c:
+        c.reset(R)
+        c.push(s)
+        pwr, done = c.finish()
+        for linear in (False, True):
+            f, v = c.write_data(1420405752.0, 2000000, linear=linear, baseline=base)
+            fo, vo = np.zeros(N), np.zeros(N)
+            p = pwr.copy()
+            dp = C.POINTER(C.c_double)
+            ol.oracle().rpf_oracle_write_data(N, p.ctypes.data_as(dp), done, 1420405752.0, 2000000, int(linear),
+                                              base.ctypes.data_as(dp), fo.ctypes.data_as(dp), vo.ctypes.data_as(dp))
+            assert np.array_equal(f, fo)
+            assert np.allclose(v, vo, rtol=1e-13, atol=1e-13)
+        pwr2, _ = c.finish()
+        assert np.array_equal(pwr, pwr2)               # write_data leaves the accumulator untouched
