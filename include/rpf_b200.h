@@ -111,7 +111,8 @@ int64_t rpf_repeats_done(const rpf_ctx *ctx);
 int64_t rpf_fft_pointer(const rpf_ctx *ctx);
 
 /* Run the context on a caller-owned CUDA stream (a cudaStream_t passed as
- * void*; NULL restores the context's own stream).  Synchronises first. */
+ * void*).  NULL restores the context's own non-blocking stream -- to run on the
+ * legacy default stream pass cudaStreamLegacy, not 0.  Synchronises first. */
 int rpf_set_stream(rpf_ctx *ctx, void *cuda_stream);
 
 /* Message for the last error on this context (or for create failures when

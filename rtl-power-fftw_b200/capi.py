@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librpf_b200.so")
+LIB_PATH = os.environ.get("RPF_B200_LIB", os.path.join(HERE, "librpf_b200.so"))   # override: dev A/B only
 
 EXPORTED_SYMBOLS = [
     "rpf_abi_version", "rpf_create", "rpf_destroy", "rpf_reset", "rpf_push", "rpf_push_device", "rpf_sync",

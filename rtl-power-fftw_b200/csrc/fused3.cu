@@ -19,17 +19,29 @@
 #include <stdint.h>
 #include "fft_math.cuh"
 #include "rpf_internal.h"
+#include "stage_prims.cuh"
 
 namespace {
 
 constexpr int kBlock = 256;
-constexpr int kStages = 4;
+#ifndef RPF_STAGES
+#define RPF_STAGES 3                // TMA ring depth.  3 x 8 KiB keeps two CTAs/SM under the 200 KiB shared
+#endif                              // carve-out, so the L1 keeps ~28 KiB for the few spilled twiddles
+constexpr int kStages = RPF_STAGES;
 constexpr int kIterBytes = 8192;    // G * 2N for every supported N
 constexpr int kFlushEvery = 128;    // CTA iterations between float64 flushes
 
+// Development switches (A/B variants are built by `make variant`; the defaults are the product).
+#ifndef RPF_MINBLOCKS
+#define RPF_MINBLOCKS 2             // CTAs per SM the register allocator must leave room for
+#endif
+#ifndef RPF_EXCH_MODE
+#define RPF_EXCH_MODE 1             // 1: exchange 2 warp-local + split mbarrier on S1; 0: two CTA barriers
+#endif
+
 template <int N> struct Radices;
 template <> struct Radices<512>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 8;  };
-template <> struct Radices<1024> { static constexpr int R1 = 8,  R2 = 16, R3 = 8;  };
+template <> struct Radices<1024> { static constexpr int R1 = 16, R2 = 8,  R3 = 8;  };
 template <> struct Radices<2048> { static constexpr int R1 = 8,  R2 = 16, R3 = 16; };
 template <> struct Radices<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16; };
 
@@ -43,59 +55,19 @@ struct Geo {
     static constexpr int NC1 = N / R1;            // pass-1 columns (= stride of the first digit)
     static constexpr int P1 = NC1 + (R3 % 16);    // S1 row pitch (bank-conflict padding)
     static constexpr int S1_ELEMS = R1 * P1;      // per spectrum
-    static constexpr int S2_ELEMS = N;
+    static constexpr int P2 = R3 + 1;             // S2 row pitch: rows are pass-3 columns u = k1*R2 + k2
+    static constexpr int S2_ELEMS = (N / R3) * P2;
+    // Exchange 2 (pass 2 -> pass 3) only moves data between threads that share k1.  When every
+    // warp owns the same k1 set in both passes the exchange is warp-local: __syncwarp, no CTA barrier.
+    static constexpr bool WARP_LOCAL2 = RPF_EXCH_MODE && ((T == 32) || (C2 == 1 && C3 == 1 && R2 == R3));
     static constexpr size_t SMEM = 64 /*mbarriers*/ + (size_t)kStages * kIterBytes +
                                    (size_t)G * (S1_ELEMS + S2_ELEMS) * sizeof(c32);
     static_assert(G * 2 * N == kIterBytes, "8 KiB of raw bytes per CTA iteration");
     static_assert(R1 * R2 * R3 == N, "radix schedule");
 };
 
-// ---- mbarrier / TMA (1-D bulk) primitives ---------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-
-// u8 pair (I | Q<<8) -> complex float carrying a +32768 offset on both rails:
-// PRMT builds 0x4700XX00 = 32768.0f + XX exactly (byte into mantissa bits 15:8).
-// No window: the offset (32768+127 per rail) is left in; every butterfly sum of
-// <= 16 such values is an exact integer < 2^24, the offset cancels exactly in
-// every output of the first radix pass except k1 = 0, where R1*32895 is
-// subtracted exactly (fix_bias()).  Result: bit-identical to converting and
-// subtracting 127.0f per sample (src/datastore.cxx:74-75), at 2 instead of 3
-// issue slots per sample.
-__device__ __forceinline__ c32 unpack_biased(uint32_t raw)
-{
-    c32 v;
-    v.x = __uint_as_float(__byte_perm(raw, 0x47000000u, 0x7604));
-    v.y = __uint_as_float(__byte_perm(raw, 0x47000000u, 0x7614));
-    return v;
-}
-constexpr float kBias = 32768.0f + 127.0f;
-
 template <int N, bool WINDOW, bool SRC_C32>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, RPF_MINBLOCKS)
 fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx, int64_t nspec, int M,
               const float2 *__restrict__ twiddle, const float *__restrict__ window, double *__restrict__ rows)
 {
@@ -119,8 +91,12 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
     const int64_t nitems = SRC_C32 ? nspec * (int64_t)M : nspec;     // spectra-sized work items
     const int64_t niter = (nitems + G - 1) / G;
     const int64_t it0 = (niter * (int64_t)blockIdx.x) / gridDim.x;
-    const int64_t it1 = (niter * (int64_t)(blockIdx.x + 1)) / gridDim.x;
-    if (it0 >= it1) return;             // nothing for this CTA (uniform per CTA)
+    const int nit = (int)((niter * (int64_t)(blockIdx.x + 1)) / gridDim.x - it0);   // < 2^31 per CTA
+    if (nit <= 0) return;               // nothing for this CTA (uniform per CTA)
+    // group `grp` holds a real spectrum in local iterations j < jvalid (only the stream's last
+    // iteration can be partial)
+    const int64_t jv = (nitems - grp - it0 * G + G - 1) / G;
+    const int jvalid = jv < nit ? (int)jv : nit;
 
     // ---- per-thread constants: twiddles (+ window) in registers --------------
     float2 tw1[C1][R1 - 1], tw2[C2][R2 - 1];
@@ -158,7 +134,7 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
 #pragma unroll
         for (int c = 0; c < C3; c++) {
             const int u = tau + T * c;
-            const int k1 = u % R1, k2 = u / R1;
+            const int k1 = u / R2, k2 = u % R2;
 #pragma unroll
             for (int k3 = 0; k3 < R3; k3++) {
                 const int k = k1 + R1 * k2 + R1 * R2 * k3;                 // FFT output index
@@ -171,36 +147,38 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
     };
 
     // ---- TMA ring ------------------------------------------------------------
-    auto issue = [&](int64_t it) {      // called by thread 0 only
-        const int slot = (int)((it - it0) % kStages);
-        const int64_t first = it * G;
-        const int64_t nv = (nitems - first) < G ? (nitems - first) : G;
-        const uint32_t nbytes = (uint32_t)(nv * 2 * N);
+    const uint8_t *cta_bytes = SRC_C32 ? nullptr : bytes + (size_t)it0 * kIterBytes;
+    auto issue = [&](int j) {           // called by thread 0 only
+        const int slot = j % kStages;
+        const int64_t left = nitems - (it0 + j) * G;
+        const uint32_t nbytes = (uint32_t)((left < G ? left : G) * 2 * N);
         const uint32_t bar = smem_u32(&bars[slot]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar, nbytes);
-        tma_load_1d(smem_u32(ring + (size_t)slot * kIterBytes), bytes + (size_t)first * 2 * N, nbytes, bar);
+        tma_load_1d(smem_u32(ring + (size_t)slot * kIterBytes), cta_bytes + (size_t)j * kIterBytes, nbytes, bar);
     };
-    if (!SRC_C32) {
-        if (tid == 0) {
+    if (tid == 0) {
+        if (!SRC_C32) {
 #pragma unroll
             for (int s = 0; s < kStages; s++) mbar_init(smem_u32(&bars[s]), 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        __syncthreads();
-        if (tid == 0)
-            for (int s = 0; s < kStages; s++)
-                if (it0 + s < it1) issue(it0 + s);
+        mbar_init(smem_u32(&bars[kStages]), kBlock / 32);   // "S1 has been read" -- one arrival per warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    if (!SRC_C32 && tid == 0)
+        for (int s = 0; s < kStages; s++)
+            if (s < nit) issue(s);
+    const uint32_t bar_s1free = smem_u32(&bars[kStages]);
 
     int since_flush = 0;
-    for (int64_t it = it0; it < it1; it++) {
-        const int64_t item = it * G + grp;
-        const bool valid = item < nitems;
+    for (int j = 0; j < nit; j++) {
+        const bool valid = (G == 1 && !SRC_C32) ? true : (j < jvalid);
         c32 v[16];
 
         // ================= pass 1: load + radix-R1 over the high digit =========
         if (SRC_C32) {
+            const int64_t item = (it0 + j) * G + grp;
             const int ko = (int)(item / nspec);
             if (ko != kouter) { flush(); kouter = ko; since_flush = 0; }
             const int64_t spec = item - (int64_t)ko * nspec;
@@ -210,8 +188,8 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
 #pragma unroll
                 for (int n1 = 0; n1 < R1; n1++) v[c * R1 + n1] = __ldg(&src[n1 * NC1 + tau + T * c]);
         } else {
-            const int slot = (int)((it - it0) % kStages);
-            mbar_wait(smem_u32(&bars[slot]), (uint32_t)(((it - it0) / kStages) & 1));
+            const int slot = j % kStages;
+            mbar_wait(smem_u32(&bars[slot]), (uint32_t)((j / kStages) & 1));
             const uint8_t *raw = ring + (size_t)slot * kIterBytes + (size_t)grp * 2 * N;
 #pragma unroll
             for (int c = 0; c < C1; c++)
@@ -232,12 +210,16 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
             if (!SRC_C32 && !WINDOW)   // remove the R1 * (32768+127) left in output 0 -- exact
                 v[c * R1] = __fadd2_rn(v[c * R1], make_float2(-(float)R1 * kBias, -(float)R1 * kBias));
             const int t = tau + T * c;
-            s1[t] = v[c * R1];
 #pragma unroll
-            for (int k1 = 1; k1 < R1; k1++) s1[k1 * P1 + t] = cmul(v[c * R1 + k1], tw1[c][k1 - 1]);
+            for (int k1 = 1; k1 < R1; k1++) v[c * R1 + k1] = cmul(v[c * R1 + k1], tw1[c][k1 - 1]);
+            // split barrier: every warp must have finished reading S1 in the previous iteration
+            // (it arrived on bar_s1free right after its pass-2 loads, long ago)
+            if (g::WARP_LOCAL2 && c == 0 && j > 0) mbar_wait(bar_s1free, (uint32_t)((j - 1) & 1));
+#pragma unroll
+            for (int k1 = 0; k1 < R1; k1++) s1[k1 * P1 + t] = v[c * R1 + k1];
         }
-        __syncthreads();   // S1 complete; ring slot fully consumed
-        if (!SRC_C32 && tid == 0 && it + kStages < it1) issue(it + kStages);
+        __syncthreads();   // S1 complete; ring slot consumed
+        if (!SRC_C32 && tid == 0 && j + kStages < nit) issue(j + kStages);
 
         // ================= pass 2 ==============================================
 #pragma unroll
@@ -247,6 +229,10 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
 #pragma unroll
             for (int n2 = 0; n2 < R2; n2++) v[c * R2 + n2] = s1[k1 * P1 + n2 * R3 + n3];
         }
+        if (g::WARP_LOCAL2) {
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar_s1free);   // this warp's S1 reads are issued (LSU is in order)
+        }
 #pragma unroll
         for (int c = 0; c < C2; c++) {
             const int q = tau + T * c;
@@ -254,21 +240,20 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
             Dft<R2>::run(&v[c * R2]);
 #pragma unroll
             for (int k2 = 0; k2 < R2; k2++) {
-                const int f = (k1 + R1 * k2) % R3;                 // XOR swizzle: see pass 3 load
                 const c32 y = (k2 == 0) ? v[c * R2] : cmul(v[c * R2 + k2], tw2[c][k2 - 1]);
-                s2[(k1 * R2 + k2) * R3 + (n3 ^ f)] = y;
+                s2[(k1 * R2 + k2) * g::P2 + n3] = y;               // immediate offsets off one base register
             }
         }
-        __syncthreads();   // S2 complete; S1 free for the next iteration
+        // S2 rows of this warp's k1 set complete.  (When not warp-local, the CTA barrier also keeps
+        // the previous iteration's pass-3 reads ahead of these writes: see the hazard note above.)
+        if (g::WARP_LOCAL2) __syncwarp(); else __syncthreads();
 
         // ================= pass 3 + |X|^2 ======================================
 #pragma unroll
         for (int c = 0; c < C3; c++) {
-            const int u = tau + T * c;
-            const int k1 = u % R1, k2 = u / R1;
-            const int f = u % R3;                                  // == (k1 + R1*k2) % R3
+            const int u = tau + T * c;                             // = k1*R2 + k2
 #pragma unroll
-            for (int n3 = 0; n3 < R3; n3++) v[c * R3 + n3] = s2[(k1 * R2 + k2) * R3 + (n3 ^ f)];
+            for (int n3 = 0; n3 < R3; n3++) v[c * R3 + n3] = s2[u * g::P2 + n3];
         }
 #pragma unroll
         for (int c = 0; c < C3; c++) {

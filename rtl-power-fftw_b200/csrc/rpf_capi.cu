@@ -33,6 +33,7 @@ struct rpf_ctx {
     int grid = 0, groups = 1, nrows = 0;
     size_t spectrum_bytes = 0;        // 2N
     bool has_window = false;
+    bool use4096 = false;             // dedicated N=4096 kernel (also the four-step inner transform)
 
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[kNumStage] = {}, ev_consumed[kNumStage] = {};
@@ -114,7 +115,7 @@ int launch_spectra(rpf_ctx *c, const uint8_t *src, int64_t nspec)
     L.twiddle = c->d_twiddle; L.window = c->d_window; L.rows = c->d_rows;
     L.grid = c->grid; L.stream = c->stream;
     if (c->plan == PLAN_FUSED3) {
-        CU(c, rpf_launch_fused3(c->N, L));
+        CU(c, c->use4096 ? rpf_launch_fused4096(L) : rpf_launch_fused3(c->N, L));
         c->launches++;
     } else if (c->plan == PLAN_SMALL) {
         CU(c, rpf_launch_small(c->N, L));
@@ -126,7 +127,7 @@ int launch_spectra(rpf_ctx *c, const uint8_t *src, int64_t nspec)
                                             c->d_window, c->d_scratch, c->stream));
             RpfLaunch Li = L;
             Li.bytes = nullptr; Li.cplx = c->d_scratch; Li.nspec = b; Li.M = c->M; Li.window = nullptr;
-            CU(c, rpf_launch_fused3(kInnerN, Li));
+            CU(c, c->use4096 ? rpf_launch_fused4096(Li) : rpf_launch_fused3(kInnerN, Li));
             c->launches += 2;
         }
     }
@@ -178,12 +179,20 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             CU(c, cudaHostAlloc((void **)&c->h_carry[i], c->spectrum_bytes, cudaHostAllocDefault));
         }
         int inner = N;
+        const char *force = getenv("RPF_B200_FORCE_GENERIC");      // development A/B switch only
+        const bool generic = force && force[0] == '1';
         if (rpf_fused3_supported(N)) {
-            c->plan = PLAN_FUSED3; c->groups = rpf_fused3_groups(N); c->grid = 2 * sms;
+            c->plan = PLAN_FUSED3;
+            c->use4096 = (N == kInnerN) && !generic;
+            c->groups = c->use4096 ? rpf_fused4096_groups() : rpf_fused3_groups(N);
+            c->grid = c->use4096 ? sms : 2 * sms;
         } else if (N <= 256) {
             c->plan = PLAN_SMALL; c->groups = 1; c->grid = 8 * sms;
         } else {
-            c->plan = PLAN_FOURSTEP; c->M = N / kInnerN; inner = kInnerN; c->groups = 1; c->grid = 2 * sms;
+            c->plan = PLAN_FOURSTEP; c->M = N / kInnerN; inner = kInnerN;
+            c->use4096 = !generic;
+            c->groups = c->use4096 ? rpf_fused4096_groups() : 1;
+            c->grid = c->use4096 ? sms : 2 * sms;
             c->scratch_spectra = ((size_t)64 << 20) / ((size_t)N * sizeof(float2));
             if (c->scratch_spectra < 1) c->scratch_spectra = 1;
             CU(c, cudaMalloc(&c->d_scratch, (size_t)c->scratch_spectra * N * sizeof(float2)));
@@ -192,7 +201,10 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             CU(c, cudaMalloc(&c->d_twiddle_big, sizeof(float2) * N));
             CU(c, cudaMemcpy(c->d_twiddle_big, tb.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
         }
-        if (c->plan != PLAN_SMALL) CU(c, rpf_fused3_configure());
+        if (c->plan != PLAN_SMALL) {
+            CU(c, rpf_fused3_configure());
+            CU(c, rpf_fused4096_configure());
+        }
         std::vector<float2> tw;
         fill_twiddle(tw, inner);
         CU(c, cudaMalloc(&c->d_twiddle, sizeof(float2) * inner));

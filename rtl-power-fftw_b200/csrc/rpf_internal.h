@@ -22,6 +22,11 @@ int rpf_fused3_groups(int N);          // spectra per CTA iteration (G)
 bool rpf_fused3_supported(int N);
 cudaError_t rpf_fused3_configure();    // opt-in shared memory attributes (once per device)
 
+// N = 4096 specialisation (512-thread CTAs, two spectra per iteration, warp-uniform pass-2 twiddles).
+cudaError_t rpf_launch_fused4096(const RpfLaunch &L);
+cudaError_t rpf_fused4096_configure();
+int rpf_fused4096_groups();
+
 // Generic power-of-two N in [2,256]: shared-memory radix-2 Stockham.
 cudaError_t rpf_launch_small(int N, const RpfLaunch &L);
 

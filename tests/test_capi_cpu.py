@@ -1,0 +1,98 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every
+symbol include/rpf_b200.h declares, fails loudly without a GPU (no CPU
+fallback), and the synthetic source is well-formed."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from rpf import pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_header_and_library_agree():
+    hdr = open(os.path.join(ROOT, "include", "rpf_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(rpf_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared == sorted(pkg.EXPORTED_SYMBOLS)
+    lib = pkg.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (rpf_[a-z_0-9]+)", out))
+    assert set(declared) <= exported
+    assert lib.rpf_abi_version() == 1
+
+
+def test_every_entry_point_cites_the_reference():
+    hdr = open(os.path.join(ROOT, "include", "rpf_b200.h")).read()
+    for fn in ("rpf_create", "rpf_destroy", "rpf_reset", "rpf_push", "rpf_finish", "rpf_write_data"):
+        i = hdr.index("int " + fn) if ("int " + fn) in hdr else hdr.index("void " + fn)
+        assert re.search(r"src/\w+\.(cxx|h):\d+", hdr[max(0, i - 1500):i]), fn
+
+
+def test_no_oracle_in_product_path():
+    """The product may not include, link or call anything under oracle/."""
+    pk = os.path.join(ROOT, "rtl-power-fftw_b200")
+    for dp, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".h", ".cpp", ".py", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in txt.lower() or f in ("__init__.py",), (dp, f)
+    out = subprocess.run(["ldd", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "rpf_ref" not in out
+
+
+@pytest.mark.skipif(_gpu(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu():
+    with pytest.raises(pkg.RpfError) as e:
+        pkg.Context(4096)
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+    exe = os.path.join(ROOT, "rtl-power-fftw_b200", "host", "rpf_power_synth")
+    r = subprocess.run([exe, "512", "100"], capture_output=True, text=True)
+    assert r.returncode == 7                    # ReturnValue::HardwareError, as the reference would exit
+    assert "no usable CUDA device" in r.stderr
+
+
+def test_create_argument_validation_without_gpu():
+    lib = pkg.lib()
+    h = C.c_void_p()
+    assert lib.rpf_create(None, C.byref(h)) == -1
+    cfg = pkg.capi.RpfConfig()
+    cfg.N = 511
+    assert lib.rpf_create(C.byref(cfg), C.byref(h)) == -1
+    assert b"even" in lib.rpf_strerror(None)
+    cfg.N = 500
+    assert lib.rpf_create(C.byref(cfg), C.byref(h)) == -2      # valid for the reference; loud, not silent
+    lib.rpf_destroy(None)                                       # NULL allowed
+
+
+def test_synth_source_is_counter_based():
+    a = pkg.synth_fill_host(4096, 0, seed=1, mode=0)
+    for off, ln in ((0, 17), (5, 100), (8, 64), (1001, 999)):
+        assert np.array_equal(pkg.synth_fill_host(ln, off, seed=1, mode=0), a[off:off + ln])
+    assert not np.array_equal(a, pkg.synth_fill_host(4096, 0, seed=2, mode=0))
+    g = pkg.synth_fill_host(1 << 20, 0, seed=3, mode=1).astype(np.float64)
+    assert abs(g.mean() - 127.4) < 0.2 and abs(g.std() - 30.0) < 0.5
+    t = pkg.synth_fill_host(2 * 4096, 0, seed=3, mode=2).astype(np.float64)
+    z = (t[0::2] - 127) + 1j * (t[1::2] - 127)
+    assert np.argmax(np.abs(np.fft.fft(z))) == 4096 // 8        # +fs/8 tone
+
+
+def test_shard_ranges_cover_and_are_spectrum_aligned():
+    sh = pkg.sharding if hasattr(pkg, "sharding") else __import__("importlib").import_module(
+        "rtl-power-fftw_b200.sharding")
+    for total, world in ((80000000, 8), (1000003, 8), (7, 8), (100, 3)):
+        ranges = [sh.shard_range(total, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == total
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+        assert max(b - a for a, b in ranges) - min(b - a for a, b in ranges) <= 1
+    assert sh.shard_byte_range(4096, 80000000, 1, 8) == (2 * 4096 * 10000000, 2 * 4096 * 20000000)

@@ -1,0 +1,63 @@
+"""GPU tests of the reference-shaped C++ host side (rtl-power-fftw_b200/host):
+Datastore's buffer queues + worker thread calling the C ABI, Acquisition's
+producer loop and write_data's text format, driven by the synthetic source."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from rpf import pkg
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "rtl-power-fftw_b200", "host", "rpf_power_synth")
+
+
+def oracle_text(N, repeats, window, seed, mode, buf_length, linear, fs=2000000, cfreq=1420405752):
+    if not buf_length:
+        buf_length = ol.oracle().rpf_oracle_plan_buf_length(N, repeats, 1638400, 0)
+    sizes = ol.oracle_read_sizes(N, repeats, buf_length)
+    stream = pkg.synth_fill_host(int(sizes.sum()), 0, seed=seed, mode=mode)
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32) if window else None
+    pwr, done = ol.oracle_run_stream(N, repeats, stream, window=w, buf_length=buf_length)
+    f, v = np.zeros(N), np.zeros(N)
+    dp = C.POINTER(C.c_double)
+    ol.oracle().rpf_oracle_write_data(N, pwr.ctypes.data_as(dp), done, float(cfreq), fs, int(linear), None,
+                                      f.ctypes.data_as(dp), v.ctypes.data_as(dp))
+    digits = math.ceil(math.floor(math.log10(cfreq)) - math.log10(fs / N) + 1 + 2)   # src/acquisition.cxx:381-382
+    return ["%.*g" % (digits, x) for x in f], v, done, len(sizes)
+
+
+@pytest.mark.parametrize("N,repeats,window,mode,buf,linear",
+                         [(512, 100, 0, 1, 0, 0),            # BASELINE config 1
+                          (4096, 450, 1, 2, 1638400, 0),     # window-fused prologue, 3 buffers
+                          (65536, 30, 0, 1, 1638400, 1),     # straddling spectra, linear output
+                          (2048, 64, 0, 0, 16384 * 3, 0)])
+def test_one_hop_text_output(N, repeats, window, mode, buf, linear):
+    seed = 0x5EED + N
+    r = subprocess.run([EXE, str(N), str(repeats), str(window), str(seed), str(mode), str(buf), "5", str(linear)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    rows = [ln.split() for ln in r.stdout.splitlines() if ln and not ln.startswith("#")]
+    assert len(rows) == N
+    ftxt, v, done, nreads = oracle_text(N, repeats, window, seed, mode, buf, linear)
+    assert [a for a, _ in rows] == ftxt                                   # frequency column: identical text
+    got = np.array([float(b) for _, b in rows])
+    if linear:
+        assert np.max(np.abs(got - v) / np.abs(v)) < 2e-5                 # 6 significant digits printed
+    else:
+        assert np.max(np.abs(got - v)) < 2e-4                             # dB: 1e-5 relative ~ 4e-5 dB + print rounding
+    assert "Actual number of averaged spectra: %d" % done in r.stderr
+    assert "Actual number of device readouts: %d" % nreads in r.stderr
+    hist = [ln for ln in r.stderr.splitlines() if ln.startswith("Buffer queue histogram:")]
+    assert hist and sum(int(x) for x in hist[0].split(":")[1].split()) == nreads
+    assert r.stdout.startswith("# rtl-power-fftw output")
+
+
+def test_invalid_bins_exit_code():
+    r = subprocess.run([EXE, "500", "10"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3 and "not supported" in r.stderr             # ReturnValue::InvalidArgument
