@@ -32,6 +32,14 @@ constexpr int kBlock4 = kT * kG;      // 512
 #define RPF4096_STAGES 3
 #endif
 constexpr int kStages4 = RPF4096_STAGES;
+// Ablation switches for timing experiments only (results are wrong when set):
+//   RPF_ABL & 1: skip the floating-point work; RPF_ABL & 2: skip the shared-memory exchange loads/stores
+//   (barriers stay: the TMA ring protocol needs them).
+#ifndef RPF_ABL
+#define RPF_ABL 0
+#endif
+#define ABL_FP(x)   do { if (!(RPF_ABL & 1)) { x; } } while (0)
+#define ABL_MEM(x)  do { if (!(RPF_ABL & 2)) { x; } } while (0)
 constexpr int kSlotBytes = kG * 2 * kN;   // 16 KiB
 constexpr int kFlushEvery4 = 128;         // iterations between float64 flushes (fp32 partial sums of <= 128 spectra)
 constexpr int kHdr4 = 128;                // mbarriers; keeps S1 128-byte aligned for the XOR swizzle
@@ -163,36 +171,37 @@ fused4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ c
                 v[n1] = x;
             }
         }
-        Dft<16>::run(v);
+        ABL_FP(Dft<16>::run(v));
         if (!SRC_C32 && !WINDOW)     // remove the 16 * (32768 + 127) left in output 0 -- exact
             v[0] = __fadd2_rn(v[0], make_float2(-16.0f * kBias, -16.0f * kBias));
 #pragma unroll
-        for (int k1 = 1; k1 < 16; k1++) v[k1] = cmul(v[k1], tw1[k1 - 1]);
+        for (int k1 = 1; k1 < 16; k1++) ABL_FP(v[k1] = cmul(v[k1], tw1[k1 - 1]));
 #pragma unroll
         for (int u = 0; u < 8; u++)  // row t of S1: 16-byte units (k1 = 2u, 2u+1), unit index XOR (t & 7)
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s1_st ^ (u << 4)), "f"(v[2 * u].x),
-                         "f"(v[2 * u].y), "f"(v[2 * u + 1].x), "f"(v[2 * u + 1].y) : "memory");
+            ABL_MEM(asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s1_st ^ (u << 4)), "f"(v[2 * u].x),
+                         "f"(v[2 * u].y), "f"(v[2 * u + 1].x), "f"(v[2 * u + 1].y) : "memory"));
         __syncthreads();             // S1 complete; ring slot consumed; S2 of the previous iteration fully read
         if (!SRC_C32 && tid == 0 && j + kStages4 < nit) issue(j + kStages4);
 
         // ================= pass 2: radix-16 over n2; this warp owns n3 ===========================
 #pragma unroll
         for (int n2 = 0; n2 < 16; n2++)
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[n2].x), "=f"(v[n2].y) : "r"(s1_ld + n2 * 2048));
-        Dft<16>::run(v);
+            ABL_MEM(asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[n2].x), "=f"(v[n2].y) : "r"(s1_ld + n2 * 2048)));
+        ABL_FP(Dft<16>::run(v));
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
             c32 y = v[k2];
-            if (k2 > 0) y = cmul(y, c_tw2_4096[n3][k2]);                  // warp-uniform operand
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(s2_st + k2 * 2048), "f"(y.x), "f"(y.y) : "memory");
+            if (k2 > 0) ABL_FP(y = cmul(y, c_tw2_4096[n3][k2]));          // warp-uniform operand
+            ABL_MEM(asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(s2_st + k2 * 2048), "f"(y.x), "f"(y.y) : "memory"));
+            if (RPF_ABL & 2) v[k2] = y;
         }
         __syncthreads();             // S2 complete; S1 free for the next iteration
 
         // ================= pass 3: radix-16 over n3, |X|^2 ========================================
 #pragma unroll
         for (int m = 0; m < 16; m++)
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[m].x), "=f"(v[m].y) : "r"(s2_ld + m * 128));
-        Dft<16>::run(v);
+            ABL_MEM(asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[m].x), "=f"(v[m].y) : "r"(s2_ld + m * 128)));
+        ABL_FP(Dft<16>::run(v));
         if (j < jvalid) {
 #pragma unroll
             for (int k3 = 0; k3 < 16; k3++) acc[k3] = fmaf(v[k3].x, v[k3].x, fmaf(v[k3].y, v[k3].y, acc[k3]));
