@@ -149,3 +149,38 @@ template <> struct Dft<8> {
 template <> struct Dft<16> {
     static __device__ __forceinline__ void run(c32 *x) { dft_composite<4, 4>(x); }
 };
+
+// Radix-16 in two halves, so that a caller can issue independent memory operations in between
+// (software pipelining).  dft16_first: 4 radix-4 butterflies over n1 (x[4 n1 + n0]) + the internal
+// W_16^{n0 k0} twiddles, result a[n0][k0] left in x[4 k0 + n0].  dft16_second: 4 radix-4 butterflies
+// over n0, result X[k0 + 4 k1] in natural order.  dft16_first followed by dft16_second == Dft<16>::run.
+__device__ __forceinline__ void dft16_first(c32 *x)
+{
+    c32 a[16];
+#pragma unroll
+    for (int n0 = 0; n0 < 4; n0++) {
+        c32 col[4] = {x[n0], x[4 + n0], x[8 + n0], x[12 + n0]};
+        Dft<4>::run(col);
+#pragma unroll
+        for (int k0 = 0; k0 < 4; k0++) a[4 * k0 + n0] = col[k0];
+    }
+    // a[4 k0 + n0] *= W_16^{n0 k0}
+    a[4 * 1 + 1] = mul_w16<1>(a[4 * 1 + 1]); a[4 * 1 + 2] = mul_w16<2>(a[4 * 1 + 2]); a[4 * 1 + 3] = mul_w16<3>(a[4 * 1 + 3]);
+    a[4 * 2 + 1] = mul_w16<2>(a[4 * 2 + 1]); a[4 * 2 + 2] = mul_w16<4>(a[4 * 2 + 2]); a[4 * 2 + 3] = mul_w16<6>(a[4 * 2 + 3]);
+    a[4 * 3 + 1] = mul_w16<3>(a[4 * 3 + 1]); a[4 * 3 + 2] = mul_w16<6>(a[4 * 3 + 2]); a[4 * 3 + 3] = mul_w16<9>(a[4 * 3 + 3]);
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = a[i];
+}
+__device__ __forceinline__ void dft16_second(c32 *x)
+{
+    c32 y[16];
+#pragma unroll
+    for (int k0 = 0; k0 < 4; k0++) {
+        c32 row[4] = {x[4 * k0], x[4 * k0 + 1], x[4 * k0 + 2], x[4 * k0 + 3]};
+        Dft<4>::run(row);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; k1++) y[k0 + 4 * k1] = row[k1];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = y[i];
+}

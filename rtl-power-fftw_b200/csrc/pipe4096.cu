@@ -1,0 +1,266 @@
+// pipe4096.cu -- N = 4096, two-stream software pipeline.
+//
+// Same arithmetic and shared-memory layouts as fused4096.cu, different schedule.  The butterflies
+// keep the FP32 pipe ~95 % busy when nothing interferes (tools/dftbench.cu), and the staging +
+// exchange traffic alone would run at > 28 % of the HBM roofline, but a CTA whose warps all move
+// through load -> butterfly -> store -> barrier in lock-step serialises the two.  Here every thread
+// carries TWO spectra (streams A and B, 16 values each) and alternates between them:
+//
+//     stage(Y,p):  first half of the radix-16 on Y
+//                  wait(mbarrier of X's next pass);  issue X's 16 loads      <- hidden under Y's math
+//                  second half of the radix-16 on Y;  twiddle;  store Y;  arrive(mbarrier of Y's pass)
+//
+// with the stage order (A,1)(B,1)(A,2)(B,2)(A,3)(B,3).  Barriers are split mbarrier arrive/wait
+// pairs with half a butterfly of slack, so no warp ever sits in bar.sync; loads have half a
+// butterfly plus the twiddle/store tail to land.  One CTA = 256 threads per SM, <= 255 registers,
+// both twiddle sets in registers, no spills.
+//
+// Replaces reference src/datastore.cxx:68-87 for N = 4096.
+#include <stdint.h>
+#include "fft_math.cuh"
+#include "rpf_internal.h"
+#include "stage_prims.cuh"
+
+namespace {
+
+constexpr int kN = 4096;
+constexpr int kThreads = 256;
+#ifndef RPF_PIPE_STAGES
+#define RPF_PIPE_STAGES 3
+#endif
+constexpr int kStagesP = RPF_PIPE_STAGES;         // TMA ring depth per stream
+constexpr int kSpecBytes = 2 * kN;                // 8 KiB
+constexpr int kFlushPairs = 64;                   // flush every 64 iterations = 128 spectra
+constexpr int kHdrP = 128;
+constexpr int kS1Off = kHdrP + 2 * kStagesP * kSpecBytes;
+constexpr int kS2Off = kS1Off + 2 * kN * 8;
+constexpr size_t kSmemP = (size_t)kS2Off + 2 * kN * 8;
+
+// barrier indices inside the header
+__device__ __forceinline__ constexpr int bar_full(int s, int slot) { return s * kStagesP + slot; }
+__device__ __forceinline__ constexpr int bar_rd(int s, int e) { return 2 * kStagesP + s * 2 + (e - 1); }
+
+__device__ __forceinline__ void lds16x16(uint32_t base, uint32_t (&raw)[16])
+{
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(raw[n1]) : "r"(base + n1 * 512));
+}
+template <int STRIDE>
+__device__ __forceinline__ void lds64x16(uint32_t base, c32 (&v)[16])
+{
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[i].x), "=f"(v[i].y) : "r"(base + i * STRIDE));
+}
+__device__ __forceinline__ void sts_s1(uint32_t base, const c32 (&v)[16])
+{
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base ^ (u << 4)), "f"(v[2 * u].x), "f"(v[2 * u].y),
+                     "f"(v[2 * u + 1].x), "f"(v[2 * u + 1].y) : "memory");
+}
+__device__ __forceinline__ void sts_s2(uint32_t base, const c32 (&v)[16])
+{
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++)
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(base + k2 * 2048), "f"(v[k2].x), "f"(v[k2].y) : "memory");
+}
+__device__ __forceinline__ void warp_arrive(uint32_t bar)
+{
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+
+template <bool WINDOW>
+__global__ void __launch_bounds__(kThreads, 1)
+pipe4096_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__restrict__ twiddle,
+                const float *__restrict__ window, double *__restrict__ rows)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sm = smem_u32(smem);
+    const int tid = threadIdx.x;
+    const int lo = tid & 15, hi = tid >> 4;       // pass 2: (k1 = lo, n3 = hi); pass 3: (k1 = lo, k2 = hi)
+
+    // ---- work range: spectrum pairs ----------------------------------------------------
+    const int64_t npairs = (nspec + 1) / 2;
+    const int64_t p0 = (npairs * (int64_t)blockIdx.x) / gridDim.x;
+    const int nit = (int)((npairs * (int64_t)(blockIdx.x + 1)) / gridDim.x - p0);
+    if (nit <= 0) return;
+    // stream B of the last pair of the stream may not exist
+    const bool lastB_missing = (p0 + nit) * 2 > nspec;
+
+    // ---- per-thread constants ----------------------------------------------------------------
+    float2 tw1[15], tw2[15];
+#pragma unroll
+    for (int k = 1; k < 16; k++) {
+        tw1[k - 1] = twiddle[(tid * k) & (kN - 1)];             // W_4096^{t k1}, t = tid
+        tw2[k - 1] = twiddle[(hi * k * 16) & (kN - 1)];         // W_256^{n3 k2}, n3 = hi
+    }
+    float win[WINDOW ? 16 : 1];
+    if (WINDOW) {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) win[n1] = window[n1 * 256 + tid];
+    }
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = 0.0f;
+
+    // shared-memory addresses (stream B = +kSpecBytes in the ring, +32 KiB in S1/S2)
+    const uint32_t ring = sm + kHdrP;                            // [stream][slot][8 KiB]
+    const uint32_t raw_off = 2 * tid;                            // + n1 * 512
+    const uint32_t s1_st = sm + kS1Off + tid * 128 + ((tid & 7) << 4);
+    const uint32_t s1_ld = sm + kS1Off + hi * 128 + ((((lo >> 1) ^ (hi & 7)) << 4) | ((lo & 1) << 3));   // + n2 * 2048
+    const uint32_t s2_st = sm + kS2Off + hi * 128 + lo * 8;                                              // + k2 * 2048
+    const uint32_t s2_ld = sm + kS2Off + hi * 2048 + lo * 8;                                             // + n3 * 128
+    constexpr uint32_t kStreamS = kN * 8;                        // S1/S2 stream stride
+
+    double *row = rows + (size_t)blockIdx.x * kN;
+    auto flush = [&]() {
+        double cur[16];
+#pragma unroll
+        for (int k3 = 0; k3 < 16; k3++) cur[k3] = row[(tid + 256 * k3 + kN / 2) & (kN - 1)];
+#pragma unroll
+        for (int k3 = 0; k3 < 16; k3++) {
+            row[(tid + 256 * k3 + kN / 2) & (kN - 1)] = cur[k3] + (double)acc[k3];   // bin k = tid + 256 k3, fftshifted
+            acc[k3] = 0.0f;
+        }
+    };
+
+    // ---- TMA: one 8 KiB bulk copy per (stream, iteration) ------------------------------------
+    const uint8_t *cta_bytes = bytes + (size_t)p0 * 2 * kSpecBytes;
+    auto issue = [&](int s, int j) {                 // thread 0 only; spectrum 2 (p0 + j) + s
+        if (s == 1 && lastB_missing && j == nit - 1) return;
+        const int slot = j % kStagesP;
+        const uint32_t bar = sm + 8 * bar_full(s, slot);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, kSpecBytes);
+        tma_load_1d(ring + (s * kStagesP + slot) * kSpecBytes, cta_bytes + ((size_t)2 * j + s) * kSpecBytes, kSpecBytes, bar);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 2 * kStagesP; i++) mbar_init(sm + 8 * i, 1);
+#pragma unroll
+        for (int i = 0; i < 4; i++) mbar_init(sm + 8 * (2 * kStagesP + i), kThreads / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int j = 0; j < kStagesP && j < nit; j++) { issue(0, j); issue(1, j); }
+
+    c32 vA[16], vB[16];
+    uint32_t raw[16];
+
+    auto unpack = [&](c32 (&v)[16]) {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            c32 x = unpack_biased(raw[n1]);
+            if (WINDOW) {        // (u8 - 127.0f) * w, one rounding per rail: src/datastore.cxx:75-77
+                x = __fadd2_rn(x, make_float2(-kBias, -kBias));
+                x = __fmul2_rn(x, make_float2(win[n1], win[n1]));
+            }
+            v[n1] = x;
+        }
+    };
+    auto post1 = [&](c32 (&v)[16], int s) {          // bias fix, W_4096^{t k1}, store row t of S1[s], arrive
+        if (!WINDOW) v[0] = __fadd2_rn(v[0], make_float2(-16.0f * kBias, -16.0f * kBias));
+#pragma unroll
+        for (int k = 1; k < 16; k++) v[k] = cmul(v[k], tw1[k - 1]);
+        sts_s1(s1_st + s * kStreamS, v);
+        warp_arrive(sm + 8 * bar_rd(s, 1));
+    };
+    auto post2 = [&](c32 (&v)[16], int s) {          // W_256^{n3 k2}, store S2[s], arrive
+#pragma unroll
+        for (int k = 1; k < 16; k++) v[k] = cmul(v[k], tw2[k - 1]);
+        sts_s2(s2_st + s * kStreamS, v);
+        warp_arrive(sm + 8 * bar_rd(s, 2));
+    };
+    auto power = [&](const c32 (&v)[16]) {
+#pragma unroll
+        for (int k3 = 0; k3 < 16; k3++) acc[k3] = fmaf(v[k3].x, v[k3].x, fmaf(v[k3].y, v[k3].y, acc[k3]));
+    };
+
+    // prologue: raw bytes of stream A, iteration 0
+    mbar_wait(sm + 8 * bar_full(0, 0), 0);
+    lds16x16(ring + raw_off, raw);
+
+    int since_flush = 0;
+    for (int j = 0; j < nit; j++) {
+        const int slot = j % kStagesP;
+        const uint32_t ph = (uint32_t)(j & 1);
+        const bool haveB = !(lastB_missing && j == nit - 1);
+
+        // ---- (A,1)  | prefetch raw B ---------------------------------------------------------
+        unpack(vA);
+        dft16_first(vA);
+        if (haveB) {
+            mbar_wait(sm + 8 * bar_full(1, slot), (uint32_t)((j / kStagesP) & 1));
+            lds16x16(ring + (kStagesP + slot) * kSpecBytes + raw_off, raw);
+        }
+        dft16_second(vA);
+        post1(vA, 0);
+
+        // ---- (B,1)  | prefetch S1[A] ----------------------------------------------------------
+        unpack(vB);
+        dft16_first(vB);
+        mbar_wait(sm + 8 * bar_rd(0, 1), ph);         // every warp has stored its (A,1) rows
+        if (tid == 0 && j + kStagesP < nit) issue(0, j + kStagesP);   // ... so A's ring slot is free
+        lds64x16<2048>(s1_ld, vA);
+        dft16_second(vB);
+        post1(vB, 1);
+
+        // ---- (A,2)  | prefetch S1[B] ----------------------------------------------------------
+        dft16_first(vA);
+        mbar_wait(sm + 8 * bar_rd(1, 1), ph);
+        if (tid == 0 && j + kStagesP < nit) issue(1, j + kStagesP);
+        lds64x16<2048>(s1_ld + kStreamS, vB);
+        dft16_second(vA);
+        post2(vA, 0);
+
+        // ---- (B,2)  | prefetch S2[A] ----------------------------------------------------------
+        dft16_first(vB);
+        mbar_wait(sm + 8 * bar_rd(0, 2), ph);
+        lds64x16<128>(s2_ld, vA);
+        dft16_second(vB);
+        post2(vB, 1);
+
+        // ---- (A,3)  | prefetch S2[B] ----------------------------------------------------------
+        dft16_first(vA);
+        mbar_wait(sm + 8 * bar_rd(1, 2), ph);
+        lds64x16<128>(s2_ld + kStreamS, vB);
+        dft16_second(vA);
+        power(vA);
+
+        // ---- (B,3)  | prefetch raw A of the next iteration ------------------------------------
+        dft16_first(vB);
+        if (j + 1 < nit) {
+            mbar_wait(sm + 8 * bar_full(0, (j + 1) % kStagesP), (uint32_t)(((j + 1) / kStagesP) & 1));
+            lds16x16(ring + ((j + 1) % kStagesP) * kSpecBytes + raw_off, raw);
+        }
+        dft16_second(vB);
+        if (haveB) power(vB);
+
+        if (++since_flush == kFlushPairs) { flush(); since_flush = 0; }
+    }
+    flush();
+}
+
+}  // namespace
+
+cudaError_t rpf_pipe4096_configure()
+{
+    cudaError_t e = cudaFuncSetAttribute(pipe4096_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemP);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(pipe4096_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemP);
+}
+
+cudaError_t rpf_launch_pipe4096(const RpfLaunch &L)
+{
+    const int64_t npairs = (L.nspec + 1) / 2;
+    if (npairs <= 0) return cudaSuccess;
+    dim3 grid((unsigned)(npairs < L.grid ? npairs : L.grid)), block(kThreads);
+    if (L.window)
+        pipe4096_kernel<true><<<grid, block, kSmemP, L.stream>>>(L.bytes, L.nspec, L.twiddle, L.window, L.rows);
+    else
+        pipe4096_kernel<false><<<grid, block, kSmemP, L.stream>>>(L.bytes, L.nspec, L.twiddle, nullptr, L.rows);
+    return cudaGetLastError();
+}

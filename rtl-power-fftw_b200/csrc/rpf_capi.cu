@@ -34,6 +34,7 @@ struct rpf_ctx {
     size_t spectrum_bytes = 0;        // 2N
     bool has_window = false;
     bool use4096 = false;             // dedicated N=4096 kernel (also the four-step inner transform)
+    bool usepipe = false;             // N=4096 from bytes: two-stream software-pipelined kernel
 
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[kNumStage] = {}, ev_consumed[kNumStage] = {};
@@ -115,7 +116,7 @@ int launch_spectra(rpf_ctx *c, const uint8_t *src, int64_t nspec)
     L.twiddle = c->d_twiddle; L.window = c->d_window; L.rows = c->d_rows;
     L.grid = c->grid; L.stream = c->stream;
     if (c->plan == PLAN_FUSED3) {
-        CU(c, c->use4096 ? rpf_launch_fused4096(L) : rpf_launch_fused3(c->N, L));
+        CU(c, c->usepipe ? rpf_launch_pipe4096(L) : c->use4096 ? rpf_launch_fused4096(L) : rpf_launch_fused3(c->N, L));
         c->launches++;
     } else if (c->plan == PLAN_SMALL) {
         CU(c, rpf_launch_small(c->N, L));
@@ -179,13 +180,16 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             CU(c, cudaHostAlloc((void **)&c->h_carry[i], c->spectrum_bytes, cudaHostAllocDefault));
         }
         int inner = N;
-        const char *force = getenv("RPF_B200_FORCE_GENERIC");      // development A/B switch only
-        const bool generic = force && force[0] == '1';
+        // development A/B switches only: RPF_B200_KERNEL=generic|fused4096 selects an older N=4096 kernel
+        const char *kname = getenv("RPF_B200_KERNEL");
+        const bool generic = kname && !strcmp(kname, "generic");
+        const bool lockstep = kname && !strcmp(kname, "fused4096");
         if (rpf_fused3_supported(N)) {
             c->plan = PLAN_FUSED3;
-            c->use4096 = (N == kInnerN) && !generic;
-            c->groups = c->use4096 ? rpf_fused4096_groups() : rpf_fused3_groups(N);
-            c->grid = c->use4096 ? sms : 2 * sms;
+            c->usepipe = (N == kInnerN) && !generic && !lockstep;
+            c->use4096 = (N == kInnerN) && lockstep;
+            c->groups = c->usepipe ? 1 : c->use4096 ? rpf_fused4096_groups() : rpf_fused3_groups(N);
+            c->grid = (c->usepipe || c->use4096) ? sms : 2 * sms;
         } else if (N <= 256) {
             c->plan = PLAN_SMALL; c->groups = 1; c->grid = 8 * sms;
         } else {
@@ -204,6 +208,7 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
         if (c->plan != PLAN_SMALL) {
             CU(c, rpf_fused3_configure());
             CU(c, rpf_fused4096_configure());
+            CU(c, rpf_pipe4096_configure());
         }
         std::vector<float2> tw;
         fill_twiddle(tw, inner);

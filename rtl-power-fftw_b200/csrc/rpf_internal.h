@@ -27,6 +27,10 @@ cudaError_t rpf_launch_fused4096(const RpfLaunch &L);
 cudaError_t rpf_fused4096_configure();
 int rpf_fused4096_groups();
 
+// N = 4096, two-stream software pipeline (256-thread CTAs, two spectra per thread): the product path.
+cudaError_t rpf_launch_pipe4096(const RpfLaunch &L);
+cudaError_t rpf_pipe4096_configure();
+
 // Generic power-of-two N in [2,256]: shared-memory radix-2 Stockham.
 cudaError_t rpf_launch_small(int N, const RpfLaunch &L);
 
