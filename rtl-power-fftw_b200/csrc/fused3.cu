@@ -66,9 +66,6 @@ struct Geo {
     static_assert(R1 * R2 * R3 == N, "radix schedule");
 };
 
-#ifdef RPF_STAGGER_CYCLES
-__device__ int rpf_stagger_counters[256];
-#endif
 template <int N, bool WINDOW, bool SRC_C32>
 __global__ void __launch_bounds__(kBlock, RPF_MINBLOCKS)
 fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx, int64_t nspec, int M,
@@ -174,21 +171,6 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
             if (s < nit) issue(s);
     const uint32_t bar_s1free = smem_u32(&bars[kStages]);
 
-#ifdef RPF_STAGGER_CYCLES
-    {   // experiment: the second CTA to arrive on an SM starts late (rows[] tail is abused as per-SM counters)
-        __shared__ int order;
-        if (tid == 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            order = atomicAdd(reinterpret_cast<int *>(rpf_stagger_counters) + smid, 1);
-        }
-        __syncthreads();
-        if (order & 1) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < RPF_STAGGER_CYCLES) { }
-        }
-    }
-#endif
     int since_flush = 0;
     for (int j = 0; j < nit; j++) {
         const bool valid = (G == 1 && !SRC_C32) ? true : (j < jvalid);

@@ -31,6 +31,10 @@ int rpf_fused4096_groups();
 cudaError_t rpf_launch_pipe4096(const RpfLaunch &L);
 cudaError_t rpf_pipe4096_configure();
 
+// N = 4096, two warp-groups per CTA alternating on the FP32 pipe (512-thread CTAs).
+cudaError_t rpf_launch_pingpong4096(const RpfLaunch &L);
+cudaError_t rpf_pingpong4096_configure();
+
 // Generic power-of-two N in [2,256]: shared-memory radix-2 Stockham.
 cudaError_t rpf_launch_small(int N, const RpfLaunch &L);
 

@@ -65,3 +65,16 @@ __device__ __forceinline__ c32 unpack_biased(uint32_t raw)
 }
 constexpr float kBias = 32768.0f + 127.0f;
 
+
+// Compiler scheduling fence for 16 complex registers: the values must be materialised here and
+// nothing that uses them afterwards can be hoisted above this point (asm volatile statements keep
+// their relative order, so this pins butterfly code to one side of a bar.sync / bar.arrive).
+__device__ __forceinline__ void pin16(c32 (&v)[16])
+{
+    asm volatile("" : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[2].x), "+f"(v[2].y), "+f"(v[3].x),
+                      "+f"(v[3].y), "+f"(v[4].x), "+f"(v[4].y), "+f"(v[5].x), "+f"(v[5].y), "+f"(v[6].x), "+f"(v[6].y),
+                      "+f"(v[7].x), "+f"(v[7].y) :: "memory");
+    asm volatile("" : "+f"(v[8].x), "+f"(v[8].y), "+f"(v[9].x), "+f"(v[9].y), "+f"(v[10].x), "+f"(v[10].y), "+f"(v[11].x),
+                      "+f"(v[11].y), "+f"(v[12].x), "+f"(v[12].y), "+f"(v[13].x), "+f"(v[13].y), "+f"(v[14].x), "+f"(v[14].y),
+                      "+f"(v[15].x), "+f"(v[15].y) :: "memory");
+}
