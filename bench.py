@@ -16,7 +16,7 @@ Weak scaling: every rank integrates its own 1e6-spectra shard (config 5 shape).
   e2e        : the same metric through the reference-facing C ABI with HOST
                buffers (pinned), host->device copies and the pwr[] read-back
                inside the timed region.
-  roofline   : dominant kernel (fused4096_kernel): 2 B x samples per launch /
+  roofline   : dominant kernel (pipe4096_kernel): 2 B x samples per launch /
                its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline / --impl reference: the reference's own worker
                (src/datastore.cxx compiled from /root/reference into
@@ -368,7 +368,7 @@ def main():
             "config": workload_config(world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                         "kernel": "fused4096_kernel", "kernel_ms_per_launch": kern_ms,
+                         "kernel": "pipe4096_kernel", "kernel_ms_per_launch": kern_ms,
                          "algorithmic_bytes_per_launch": 2 * nspec * N_BINS,
                          "note": "2 B per complex sample; FP32-issue and shared-memory bounds in DESIGN.md"},
             "e2e": e2e, "gpu_launches": int(launches) * world, "clocks": clocks,

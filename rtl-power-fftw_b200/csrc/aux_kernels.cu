@@ -113,6 +113,22 @@ __global__ void reduce_rows_kernel(const double *__restrict__ rows, int nrows, i
     pwr[i] = s;
 }
 
+// Four-step: rows[c][k] holds sum |X|^2 of FFT index k of the inner transform for outer bin ko = c % M.
+// pwr[i] (reference order, DC at N/2) = sum over the CTAs bound to that ko, fixed order.
+__global__ void reduce_rows_fourstep_kernel(const double *__restrict__ rows, int nrows, int M, int inner,
+                                            double *__restrict__ pwr)
+{
+    const int64_t n = (int64_t)M * inner;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t bin = (i + n / 2) & (n - 1);          // undo the fftshift: i = (bin + n/2) mod n
+    const int ko = (int)(bin % M);
+    const int64_t k = bin / M;
+    double s = 0.0;
+    for (int c = ko; c < nrows; c += M) s += rows[(size_t)c * inner + k];
+    pwr[i] = s;
+}
+
 __global__ void synth_kernel(uint8_t *bytes, size_t len, uint64_t off, uint64_t seed, int mode)
 {
     // word-aligned body; bytes[i] is stream byte off+i
@@ -176,6 +192,13 @@ cudaError_t rpf_launch_fourstep_outer(int M, const uint8_t *bytes, int64_t nspec
 cudaError_t rpf_launch_reduce_rows(const double *rows, int nrows, int64_t rowlen, double *pwr, cudaStream_t stream)
 {
     reduce_rows_kernel<<<(unsigned)((rowlen + 255) / 256), 256, 0, stream>>>(rows, nrows, rowlen, pwr);
+    return cudaGetLastError();
+}
+
+cudaError_t rpf_launch_reduce_rows_fourstep(const double *rows, int nrows, int M, int inner, double *pwr, cudaStream_t stream)
+{
+    const int64_t n = (int64_t)M * inner;
+    reduce_rows_fourstep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rows, nrows, M, inner, pwr);
     return cudaGetLastError();
 }
 

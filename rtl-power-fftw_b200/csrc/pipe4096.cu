@@ -79,10 +79,17 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar)
     if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 
-template <bool WINDOW>
+// SRC_C32 = false: spectra come as raw bytes (TMA ring), bins are flushed fftshifted.
+// SRC_C32 = true : the inner transform of the four-step path (N = M * 4096).  Input rows are complex64
+//   scratch[spec][ko][4096]; CTA c is bound to ONE outer bin ko = c % M for its whole life and to the
+//   spectra spec = part, part + P, ... (part = c / M, P = gridDim / M) of the batch, so its private
+//   accumulator row is just 4096 doubles in natural order k (L2 resident, coalesced);
+//   reduce_rows_fourstep() maps (ko, k) -> bin ko + M k.  The complex rows are prefetched with plain
+//   coalesced LDG.64 one stage ahead, into the registers of the idle stream.
+template <bool WINDOW, bool SRC_C32>
 __global__ void __launch_bounds__(kThreads, 1)
-pipe4096_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__restrict__ twiddle,
-                const float *__restrict__ window, double *__restrict__ rows)
+pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx, int64_t nspec, int M,
+                const float2 *__restrict__ twiddle, const float *__restrict__ window, double *__restrict__ rows)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sm = smem_u32(smem);
@@ -90,12 +97,23 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *
     const int lo = tid & 15, hi = tid >> 4;       // pass 2: (k1 = lo, n3 = hi); pass 3: (k1 = lo, k2 = hi)
 
     // ---- work range: spectrum pairs ----------------------------------------------------
-    const int64_t npairs = (nspec + 1) / 2;
-    const int64_t p0 = (npairs * (int64_t)blockIdx.x) / gridDim.x;
-    const int nit = (int)((npairs * (int64_t)(blockIdx.x + 1)) / gridDim.x - p0);
+    int64_t p0 = 0;
+    int nit;
+    bool lastB_missing;
+    const int ko = SRC_C32 ? (int)(blockIdx.x % M) : 0;
+    const int part = SRC_C32 ? (int)(blockIdx.x / M) : 0, nparts = SRC_C32 ? (int)(gridDim.x / M) : 1;
+    if (SRC_C32) {
+        // my spectra of the batch: part, part + nparts, ...  (count = mine)
+        const int mine = (int)((nspec - part + nparts - 1) / nparts);
+        nit = (mine + 1) / 2;
+        lastB_missing = (mine & 1) != 0;
+    } else {
+        const int64_t npairs = (nspec + 1) / 2;
+        p0 = (npairs * (int64_t)blockIdx.x) / gridDim.x;
+        nit = (int)((npairs * (int64_t)(blockIdx.x + 1)) / gridDim.x - p0);
+        lastB_missing = (p0 + nit) * 2 > nspec;      // stream B of the last pair of the stream may not exist
+    }
     if (nit <= 0) return;
-    // stream B of the last pair of the stream may not exist
-    const bool lastB_missing = (p0 + nit) * 2 > nspec;
 
     // ---- per-thread constants ----------------------------------------------------------------
     float2 tw1[15], tw2[15];
@@ -123,20 +141,31 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *
     constexpr uint32_t kStreamS = kN * 8;                        // S1/S2 stream stride
 
     double *row = rows + (size_t)blockIdx.x * kN;
+    constexpr int kShift = SRC_C32 ? 0 : kN / 2;     // bytes path: fftshift here; four-step: in the reduce kernel
     auto flush = [&]() {
         double cur[16];
 #pragma unroll
-        for (int k3 = 0; k3 < 16; k3++) cur[k3] = row[(tid + 256 * k3 + kN / 2) & (kN - 1)];
+        for (int k3 = 0; k3 < 16; k3++) cur[k3] = row[(tid + 256 * k3 + kShift) & (kN - 1)];
 #pragma unroll
         for (int k3 = 0; k3 < 16; k3++) {
-            row[(tid + 256 * k3 + kN / 2) & (kN - 1)] = cur[k3] + (double)acc[k3];   // bin k = tid + 256 k3, fftshifted
+            row[(tid + 256 * k3 + kShift) & (kN - 1)] = cur[k3] + (double)acc[k3];   // bin k = tid + 256 k3
             acc[k3] = 0.0f;
         }
     };
+    // four-step: row of complex64 for (stream s, local iteration j)
+    auto crow = [&](int s, int j) -> const float2 * {
+        const int64_t spec = (int64_t)part + (int64_t)nparts * (2 * j + s);
+        return cplx + ((size_t)spec * M + ko) * (size_t)kN + tid;
+    };
+    auto ldg16 = [&](const float2 *src, c32 (&v)[16]) {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) v[n1] = __ldg(src + n1 * 256);
+    };
 
     // ---- TMA: one 8 KiB bulk copy per (stream, iteration) ------------------------------------
-    const uint8_t *cta_bytes = bytes + (size_t)p0 * 2 * kSpecBytes;
+    const uint8_t *cta_bytes = SRC_C32 ? nullptr : bytes + (size_t)p0 * 2 * kSpecBytes;
     auto issue = [&](int s, int j) {                 // thread 0 only; spectrum 2 (p0 + j) + s
+        if (SRC_C32) return;
         if (s == 1 && lastB_missing && j == nit - 1) return;
         const int slot = j % kStagesP;
         const uint32_t bar = sm + 8 * bar_full(s, slot);
@@ -170,7 +199,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *
         }
     };
     auto post1 = [&](c32 (&v)[16], int s) {          // bias fix, W_4096^{t k1}, store row t of S1[s], arrive
-        if (!WINDOW) v[0] = __fadd2_rn(v[0], make_float2(-16.0f * kBias, -16.0f * kBias));
+        if (!WINDOW && !SRC_C32) v[0] = __fadd2_rn(v[0], make_float2(-16.0f * kBias, -16.0f * kBias));
 #pragma unroll
         for (int k = 1; k < 16; k++) v[k] = cmul(v[k], tw1[k - 1]);
         sts_s1(s1_st + s * kStreamS, v);
@@ -187,9 +216,13 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *
         for (int k3 = 0; k3 < 16; k3++) acc[k3] = fmaf(v[k3].x, v[k3].x, fmaf(v[k3].y, v[k3].y, acc[k3]));
     };
 
-    // prologue: raw bytes of stream A, iteration 0
-    mbar_wait(sm + 8 * bar_full(0, 0), 0);
-    lds16x16(ring + raw_off, raw);
+    // prologue: input of stream A, iteration 0
+    if (SRC_C32) {
+        ldg16(crow(0, 0), vA);
+    } else {
+        mbar_wait(sm + 8 * bar_full(0, 0), 0);
+        lds16x16(ring + raw_off, raw);
+    }
 
     int since_flush = 0;
     for (int j = 0; j < nit; j++) {
@@ -198,17 +231,21 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *
         const bool haveB = !(lastB_missing && j == nit - 1);
 
         // ---- (A,1)  | prefetch raw B ---------------------------------------------------------
-        unpack(vA);
+        if (!SRC_C32) unpack(vA);
         dft16_first(vA);
         if (haveB) {
-            mbar_wait(sm + 8 * bar_full(1, slot), (uint32_t)((j / kStagesP) & 1));
-            lds16x16(ring + (kStagesP + slot) * kSpecBytes + raw_off, raw);
+            if (SRC_C32) {
+                ldg16(crow(1, j), vB);
+            } else {
+                mbar_wait(sm + 8 * bar_full(1, slot), (uint32_t)((j / kStagesP) & 1));
+                lds16x16(ring + (kStagesP + slot) * kSpecBytes + raw_off, raw);
+            }
         }
         dft16_second(vA);
         post1(vA, 0);
 
         // ---- (B,1)  | prefetch S1[A] ----------------------------------------------------------
-        unpack(vB);
+        if (!SRC_C32) unpack(vB);
         dft16_first(vB);
         if (!(RPF_ABL & 4)) mbar_wait(sm + 8 * bar_rd(0, 1), ph);         // every warp has stored its (A,1) rows
         if (tid == 0 && j + kStagesP < nit) issue(0, j + kStagesP);   // ... so A's ring slot is free
@@ -241,8 +278,12 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *
         // ---- (B,3)  | prefetch raw A of the next iteration ------------------------------------
         dft16_first(vB);
         if (j + 1 < nit) {
-            mbar_wait(sm + 8 * bar_full(0, (j + 1) % kStagesP), (uint32_t)(((j + 1) / kStagesP) & 1));
-            lds16x16(ring + ((j + 1) % kStagesP) * kSpecBytes + raw_off, raw);
+            if (SRC_C32) {
+                ldg16(crow(0, j + 1), vA);
+            } else {
+                mbar_wait(sm + 8 * bar_full(0, (j + 1) % kStagesP), (uint32_t)(((j + 1) / kStagesP) & 1));
+                lds16x16(ring + ((j + 1) % kStagesP) * kSpecBytes + raw_off, raw);
+            }
         }
         dft16_second(vB);
         if (haveB) power(vB);
@@ -256,19 +297,26 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *
 
 cudaError_t rpf_pipe4096_configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(pipe4096_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemP);
+    cudaError_t e = cudaFuncSetAttribute(pipe4096_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemP);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(pipe4096_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemP);
+    e = cudaFuncSetAttribute(pipe4096_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemP);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(pipe4096_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemP);
 }
 
 cudaError_t rpf_launch_pipe4096(const RpfLaunch &L)
 {
+    if (L.cplx) {   // four-step inner transform: the grid is fixed (multiple of M) so CTA <-> outer bin is stable
+        if (L.nspec <= 0) return cudaSuccess;
+        pipe4096_kernel<false, true><<<L.grid, kThreads, kSmemP, L.stream>>>(nullptr, L.cplx, L.nspec, L.M, L.twiddle, nullptr, L.rows);
+        return cudaGetLastError();
+    }
     const int64_t npairs = (L.nspec + 1) / 2;
     if (npairs <= 0) return cudaSuccess;
     dim3 grid((unsigned)(npairs < L.grid ? npairs : L.grid)), block(kThreads);
     if (L.window)
-        pipe4096_kernel<true><<<grid, block, kSmemP, L.stream>>>(L.bytes, L.nspec, L.twiddle, L.window, L.rows);
+        pipe4096_kernel<true, false><<<grid, block, kSmemP, L.stream>>>(L.bytes, nullptr, L.nspec, 1, L.twiddle, L.window, L.rows);
     else
-        pipe4096_kernel<false><<<grid, block, kSmemP, L.stream>>>(L.bytes, L.nspec, L.twiddle, nullptr, L.rows);
+        pipe4096_kernel<false, false><<<grid, block, kSmemP, L.stream>>>(L.bytes, nullptr, L.nspec, 1, L.twiddle, nullptr, L.rows);
     return cudaGetLastError();
 }

@@ -31,6 +31,7 @@ struct rpf_ctx {
     PlanKind plan = PLAN_SMALL;
     int M = 1;                        // four-step outer radix
     int grid = 0, groups = 1, nrows = 0;
+    int64_t rowlen = 0;               // doubles per private accumulator row
     size_t spectrum_bytes = 0;        // 2N
     bool has_window = false;
     bool use4096 = false;             // dedicated N=4096 kernel (also the four-step inner transform)
@@ -130,7 +131,7 @@ int launch_spectra(rpf_ctx *c, const uint8_t *src, int64_t nspec)
                                             c->d_window, c->d_scratch, c->stream));
             RpfLaunch Li = L;
             Li.bytes = nullptr; Li.cplx = c->d_scratch; Li.nspec = b; Li.M = c->M; Li.window = nullptr;
-            CU(c, c->use4096 ? rpf_launch_fused4096(Li) : rpf_launch_fused3(kInnerN, Li));
+            CU(c, rpf_launch_pipe4096(Li));
             c->launches += 2;
         }
     }
@@ -197,10 +198,10 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
         } else if (N <= 256) {
             c->plan = PLAN_SMALL; c->groups = 1; c->grid = 8 * sms;
         } else {
+            // inner transform = pipe4096 in complex-source mode: every CTA is bound to one outer bin
             c->plan = PLAN_FOURSTEP; c->M = N / kInnerN; inner = kInnerN;
-            c->use4096 = !generic;
-            c->groups = c->use4096 ? rpf_fused4096_groups() : 1;
-            c->grid = c->use4096 ? sms : 2 * sms;
+            c->usepipe = true; c->groups = 1;
+            c->grid = (sms / c->M) * c->M;
             c->scratch_spectra = ((size_t)64 << 20) / ((size_t)N * sizeof(float2));
             if (c->scratch_spectra < 1) c->scratch_spectra = 1;
             CU(c, cudaMalloc(&c->d_scratch, (size_t)c->scratch_spectra * N * sizeof(float2)));
@@ -224,11 +225,12 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             CU(c, cudaMemcpy(c->d_window, cfg->window, sizeof(float) * N, cudaMemcpyHostToDevice));
         }
         c->nrows = c->grid * c->groups;
-        CU(c, cudaMalloc(&c->d_rows, sizeof(double) * (size_t)c->nrows * N));
+        c->rowlen = c->plan == PLAN_FOURSTEP ? kInnerN : N;
+        CU(c, cudaMalloc(&c->d_rows, sizeof(double) * (size_t)c->nrows * c->rowlen));
         CU(c, cudaMalloc(&c->d_pwr, sizeof(double) * N));
         CU(c, cudaMalloc(&c->d_tmp, sizeof(double) * 2 * N));
         CU(c, cudaMalloc(&c->d_baseline, sizeof(double) * N));
-        CU(c, cudaMemset(c->d_rows, 0, sizeof(double) * (size_t)c->nrows * N));
+        CU(c, cudaMemset(c->d_rows, 0, sizeof(double) * (size_t)c->nrows * c->rowlen));
         size_t hint = cfg->buf_length > 0 ? (size_t)cfg->buf_length : (size_t)16384 * 100;   // src/params.h:43
         int r = ensure_stage(c, hint + c->spectrum_bytes);
         if (r) return r;
@@ -269,7 +271,7 @@ int rpf_reset(rpf_ctx *c, int64_t repeats)
     if (!c) return RPF_ERR_INVALID_ARG;
     if (repeats < 0) return fail(c, RPF_ERR_INVALID_ARG, "rpf_reset: repeats must be >= 0");
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaMemsetAsync(c->d_rows, 0, sizeof(double) * (size_t)c->nrows * c->N, c->stream));
+    CU(c, cudaMemsetAsync(c->d_rows, 0, sizeof(double) * (size_t)c->nrows * c->rowlen, c->stream));
     c->repeats = repeats;
     c->repeats_done = 0;
     c->carry_bytes = 0;
@@ -402,7 +404,10 @@ int rpf_finish_device(rpf_ctx *c, double *pwr_out_device, int64_t *repeats_done)
     if (!c) return RPF_ERR_INVALID_ARG;
     CU(c, cudaSetDevice(c->device));
     if (pwr_out_device) {
-        CU(c, rpf_launch_reduce_rows(c->d_rows, c->nrows, c->N, pwr_out_device, c->stream));
+        if (c->plan == PLAN_FOURSTEP)
+            CU(c, rpf_launch_reduce_rows_fourstep(c->d_rows, c->nrows, c->M, kInnerN, pwr_out_device, c->stream));
+        else
+            CU(c, rpf_launch_reduce_rows(c->d_rows, c->nrows, c->N, pwr_out_device, c->stream));
         c->launches++;
     }
     if (repeats_done) *repeats_done = c->repeats_done;
@@ -447,7 +452,10 @@ int rpf_write_data(rpf_ctx *c, double tuned_freq, int32_t samplerate, int32_t li
     if (samplerate <= 0) return fail(c, RPF_ERR_INVALID_ARG, "rpf_write_data: samplerate must be > 0");
     CU(c, cudaSetDevice(c->device));
     const int N = c->N;
-    CU(c, rpf_launch_reduce_rows(c->d_rows, c->nrows, N, c->d_pwr, c->stream));
+    if (c->plan == PLAN_FOURSTEP)
+        CU(c, rpf_launch_reduce_rows_fourstep(c->d_rows, c->nrows, c->M, kInnerN, c->d_pwr, c->stream));
+    else
+        CU(c, rpf_launch_reduce_rows(c->d_rows, c->nrows, N, c->d_pwr, c->stream));
     if (baseline)
         CU(c, cudaMemcpyAsync(c->d_baseline, baseline, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
     CU(c, rpf_launch_write_data(c->d_pwr, N, c->repeats_done, tuned_freq, samplerate, linear,

@@ -45,6 +45,8 @@ cudaError_t rpf_launch_fourstep_outer(int M, const uint8_t *bytes, int64_t nspec
 // pwr[i] = sum over rows (fixed order, float64).
 cudaError_t rpf_launch_reduce_rows(const double *rows, int nrows, int64_t rowlen, double *pwr, cudaStream_t stream);
 
+cudaError_t rpf_launch_reduce_rows_fourstep(const double *rows, int nrows, int M, int inner, double *pwr, cudaStream_t stream);
+
 cudaError_t rpf_launch_synth(uint8_t *bytes, size_t len, uint64_t stream_offset, uint64_t seed, int mode,
                              cudaStream_t stream);
 
