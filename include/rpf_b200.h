@@ -34,7 +34,8 @@ extern "C" {
 typedef enum rpf_status {
     RPF_OK = 0,
     RPF_ERR_INVALID_ARG = -1,   /* NULL pointer, odd byte count, N odd or < 2 ...            */
-    RPF_ERR_UNSUPPORTED_N = -2, /* N is valid for the reference but not implemented on GPU   */
+    RPF_ERR_UNSUPPORTED_N = -2, /* N is valid for the reference but not implemented on GPU:
+                                   supported are powers of two 2..65536 and any even N <= 8190 */
     RPF_ERR_CUDA = -3,          /* a CUDA runtime call or kernel failed (message has detail) */
     RPF_ERR_NOMEM = -4,
     RPF_ERR_STATE = -5          /* call sequence error                                       */
@@ -122,7 +123,7 @@ const char *rpf_strerror(const rpf_ctx *ctx);
 /* Number of this library's kernel launches issued by the context so far. */
 int64_t rpf_kernel_launches(const rpf_ctx *ctx);
 
-/* Name of the kernel family selected for this N ("small", "fused3", "fourstep"). */
+/* Name of the kernel family selected for this N ("small", "fused3", "fourstep", "direct"). */
 const char *rpf_plan_name(const rpf_ctx *ctx);
 
 /* ---- Acquisition::write_data() arithmetic on the device ------------------

@@ -20,7 +20,7 @@ namespace {
 constexpr int kNumStage = 3;          // staging buffers in flight (copy / compute overlap)
 constexpr int kInnerN = 4096;         // inner transform length of the four-step path
 
-enum PlanKind { PLAN_SMALL, PLAN_FUSED3, PLAN_FOURSTEP };
+enum PlanKind { PLAN_SMALL, PLAN_FUSED3, PLAN_FOURSTEP, PLAN_DIRECT };
 
 thread_local char g_create_err[256] = "";
 
@@ -124,6 +124,9 @@ int launch_spectra(rpf_ctx *c, const uint8_t *src, int64_t nspec)
     } else if (c->plan == PLAN_SMALL) {
         CU(c, rpf_launch_small(c->N, L));
         c->launches++;
+    } else if (c->plan == PLAN_DIRECT) {
+        CU(c, rpf_launch_direct_dft(c->N, L));
+        c->launches++;
     } else {
         for (int64_t done = 0; done < nspec; done += c->scratch_spectra) {
             const int64_t b = (nspec - done) < c->scratch_spectra ? (nspec - done) : c->scratch_spectra;
@@ -153,9 +156,9 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
     const int N = cfg->N;
     if (N < 2 || (N & 1))
         return fail(nullptr, RPF_ERR_INVALID_ARG, "rpf_create: N=%d must be even and >= 2 (src/params.cxx:152-155)", N);
-    if (!is_pow2(N) || N > 16 * kInnerN)
+    if ((!is_pow2(N) && N > 8190) || N > 16 * kInnerN)
         return fail(nullptr, RPF_ERR_UNSUPPORTED_N,
-                    "rpf_create: N=%d not supported by the CUDA path (power of two, 2..65536)", N);
+                    "rpf_create: N=%d not supported by the CUDA path (powers of two up to 65536, other even N up to 8190)", N);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -188,7 +191,10 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
         const bool generic = kname && !strcmp(kname, "generic");
         const bool lockstep = kname && !strcmp(kname, "fused4096");
         const bool pingpong = kname && !strcmp(kname, "pingpong");
-        if (rpf_fused3_supported(N)) {
+        if (!is_pow2(N)) {
+            c->plan = PLAN_DIRECT; c->groups = 1; c->grid = 4 * sms;
+            CU(c, rpf_direct_dft_configure());
+        } else if (rpf_fused3_supported(N)) {
             c->plan = PLAN_FUSED3;
             c->usepp = (N == kInnerN) && pingpong;
             c->usepipe = (N == kInnerN) && !generic && !lockstep && !pingpong;
@@ -210,7 +216,7 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             CU(c, cudaMalloc(&c->d_twiddle_big, sizeof(float2) * N));
             CU(c, cudaMemcpy(c->d_twiddle_big, tb.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
         }
-        if (c->plan != PLAN_SMALL) {
+        if (c->plan != PLAN_SMALL && c->plan != PLAN_DIRECT) {
             CU(c, rpf_fused3_configure());
             CU(c, rpf_fused4096_configure());
             CU(c, rpf_pipe4096_configure());
@@ -432,7 +438,7 @@ int64_t rpf_kernel_launches(const rpf_ctx *c) { return c ? c->launches : 0; }
 const char *rpf_plan_name(const rpf_ctx *c)
 {
     if (!c) return "";
-    return c->plan == PLAN_SMALL ? "small" : c->plan == PLAN_FUSED3 ? "fused3" : "fourstep";
+    return c->plan == PLAN_SMALL ? "small" : c->plan == PLAN_FUSED3 ? "fused3" : c->plan == PLAN_DIRECT ? "direct" : "fourstep";
 }
 
 int rpf_set_stream(rpf_ctx *c, void *cuda_stream)

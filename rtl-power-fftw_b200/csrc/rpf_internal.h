@@ -38,6 +38,10 @@ cudaError_t rpf_pingpong4096_configure();
 // Generic power-of-two N in [2,256]: shared-memory radix-2 Stockham.
 cudaError_t rpf_launch_small(int N, const RpfLaunch &L);
 
+// Even N that is not a power of two (2 < N <= 8190): O(N^2) DFT per spectrum.
+cudaError_t rpf_launch_direct_dft(int N, const RpfLaunch &L);
+cudaError_t rpf_direct_dft_configure();
+
 // Four-step outer pass for N = M*4096: radix-M over the stride-4096 digit + twiddle.
 cudaError_t rpf_launch_fourstep_outer(int M, const uint8_t *bytes, int64_t nspec, const float2 *twiddle_big,
                                       const float *window, float2 *scratch, cudaStream_t stream);

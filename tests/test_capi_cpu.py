@@ -70,8 +70,9 @@ def test_create_argument_validation_without_gpu():
     cfg.N = 511
     assert lib.rpf_create(C.byref(cfg), C.byref(h)) == -1
     assert b"even" in lib.rpf_strerror(None)
-    cfg.N = 500
+    cfg.N = 10000
     assert lib.rpf_create(C.byref(cfg), C.byref(h)) == -2      # valid for the reference; loud, not silent
+    assert b"not supported" in lib.rpf_strerror(None)
     lib.rpf_destroy(None)                                       # NULL allowed
 
 

@@ -36,7 +36,8 @@ def oracle_text(N, repeats, window, seed, mode, buf_length, linear, fs=2000000, 
                          [(512, 100, 0, 1, 0, 0),            # BASELINE config 1
                           (4096, 450, 1, 2, 1638400, 0),     # window-fused prologue, 3 buffers
                           (65536, 30, 0, 1, 1638400, 1),     # straddling spectra, linear output
-                          (2048, 64, 0, 0, 16384 * 3, 0)])
+                          (2048, 64, 0, 0, 16384 * 3, 0),
+                          (500, 40, 1, 1, 0, 0)])            # the man page's -b 500 (direct-DFT kernel)
 def test_one_hop_text_output(N, repeats, window, mode, buf, linear):
     seed = 0x5EED + N
     r = subprocess.run([EXE, str(N), str(repeats), str(window), str(seed), str(mode), str(buf), "5", str(linear)],
@@ -59,5 +60,5 @@ def test_one_hop_text_output(N, repeats, window, mode, buf, linear):
 
 
 def test_invalid_bins_exit_code():
-    r = subprocess.run([EXE, "500", "10"], capture_output=True, text=True, timeout=120)
+    r = subprocess.run([EXE, "10000", "10"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 3 and "not supported" in r.stderr             # ReturnValue::InvalidArgument

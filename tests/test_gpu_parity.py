@@ -45,6 +45,25 @@ def test_random_bytes_all_sizes(N):
     assert np.argmax(pg) == np.argmax(po)
 
 
+@pytest.mark.parametrize("N,R", [(6, 40), (10, 33), (500, 25), (1000, 12), (3000, 4), (8190, 2)])
+def test_even_non_power_of_two_bins(N, R):
+    """The reference only forces N even (src/params.cxx:152-155; man page: -b 500)."""
+    s = stream(2 * N * R + 2 * (N // 2), seed=N)      # + half a spectrum
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32)
+    for window in (None, w):
+        with Context(N, window=window) as c:
+            assert c.plan_name == "direct"
+            c.reset(10 ** 6)
+            cut = (s.size // 6) * 2
+            c.push(s[:cut])
+            c.push(s[cut:])
+            pg, done = c.finish()
+            assert done == R and c.fft_pointer == N // 2
+        po, _ = ol.oracle_run_stream(N, R, s, window=window, buf_length=s.size)
+        assert relmax(pg, po) < TOL
+        assert np.max(np.abs(pg - po) / po) < 1e-4 and np.argmax(pg) == np.argmax(po)
+
+
 @pytest.mark.parametrize("N", [8, 512, 4096, 65536])
 def test_kat_zero_dc_nyquist_tone(N):
     z = np.full(2 * N * 2, 127, np.uint8)
@@ -162,7 +181,7 @@ def test_argument_errors():
         Context(511)
     assert e.value.code == -1
     with pytest.raises(RpfError) as e:
-        Context(500)
+        Context(10000)
     assert e.value.code == -2                         # valid for the reference, unsupported on GPU: loud
     with Context(64) as c:
         with pytest.raises(RpfError):
