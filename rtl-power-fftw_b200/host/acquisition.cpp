@@ -1,9 +1,73 @@
 #include "acquisition.h"
 
 #include <cmath>
+#include <fstream>
 #include <iomanip>
+#include <sstream>
 #include <iostream>
 #include <thread>
+
+template <typename T> std::vector<T> read_inputfile(std::istream &stream)
+{
+    std::vector<T> values;
+    std::string line;
+    while (std::getline(stream, line)) {
+        std::istringstream ls(line);
+        if ((ls >> std::ws).peek() == '#') continue;          // comment line
+        T value, last = T();
+        bool any = false;
+        while (ls >> value) { last = value; any = true; }     // keep the last number of the line
+        if (any) values.push_back(last);
+    }
+    return values;
+}
+template std::vector<float> read_inputfile<float>(std::istream &);
+template std::vector<double> read_inputfile<double>(std::istream &);
+
+AuxData::AuxData(const Params &params) { load(params, std::cin); }
+AuxData::AuxData(const Params &params, std::istream &in) { load(params, in); }
+
+void AuxData::load(const Params &params, std::istream &in)
+{
+    const std::string N = std::to_string(params.N);
+    if (params.window && params.baseline && params.window_file == "-" && params.baseline_file == "-") {
+        // Both from stdin: 2N values, window first, then baseline (the code's stated intent,
+        // src/acquisition.cxx:64-69).  NOTE: the reference computes the split point from the still
+        // empty window vector (src/acquisition.cxx:76), so there every value lands in the baseline and
+        // the window stays empty; that defect is deliberately not reproduced.
+        std::vector<double> values = read_inputfile<double>(in);
+        if ((int)values.size() != 2 * params.N)
+            throw RPFexception("Error reading window function and baseline from stdin. Expected " +
+                               std::to_string(2 * params.N) + " values, found " + std::to_string(values.size()) + ".",
+                               ReturnValue::InvalidInput);
+        for (int i = 0; i < params.N; i++) window_values.push_back((float)values[i]);
+        for (int i = params.N; i < 2 * params.N; i++) baseline_values.push_back(values[i]);
+        return;
+    }
+    auto open_and_read = [&](const std::string &file, bool as_float) {
+        std::ifstream fs;
+        std::istream *stream = &in;
+        if (file != "-") {
+            fs.open(file);
+            if (!fs.good()) throw RPFexception("Could not open " + file + ". Quitting.", ReturnValue::InvalidInput);
+            stream = &fs;
+        }
+        if (as_float) window_values = read_inputfile<float>(*stream);
+        else baseline_values = read_inputfile<double>(*stream);
+    };
+    if (params.window) {
+        open_and_read(params.window_file, true);
+        if ((int)window_values.size() != params.N)
+            throw RPFexception("Error reading window function. Expected " + N + " values, found " +
+                               std::to_string(window_values.size()) + ".", ReturnValue::InvalidInput);
+    }
+    if (params.baseline) {
+        open_and_read(params.baseline_file, false);
+        if ((int)baseline_values.size() != params.N)
+            throw RPFexception("Error reading baseline. Expected " + N + " values, found " +
+                               std::to_string(baseline_values.size()) + ".", ReturnValue::InvalidInput);
+    }
+}
 
 bool SyntheticSource::read(Buffer &buffer)
 {

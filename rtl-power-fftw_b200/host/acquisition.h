@@ -34,10 +34,22 @@ class SyntheticSource : public SampleSource {
     int mode;
 };
 
-struct AuxData {
+// Window function and baseline read from text (src/acquisition.cxx:32-156): one value per line =
+// the LAST number on the line, lines whose first non-blank character is '#' are comments, lines
+// without a number are skipped; exactly N values are required (RPFexception, InvalidInput).
+// Window values are float, baseline values double (src/acquisition.h:33-41).
+class AuxData {
+  public:
+    AuxData() {}
+    explicit AuxData(const Params &params);            // reads params.window_file / baseline_file
+    AuxData(const Params &params, std::istream &in);   // as above with `in` standing for stdin ("-")
     std::vector<double> baseline_values;
     std::vector<float> window_values;
+  private:
+    void load(const Params &params, std::istream &in);
 };
+
+template <typename T> std::vector<T> read_inputfile(std::istream &stream);
 
 class Plan {
   public:

@@ -35,7 +35,9 @@ struct Params {
     bool buf_length_isSet = false;
     int64_t repeats = buf_length / (2 * 512);
     bool window = false;
+    std::string window_file;                           // "-" = stdin
     bool baseline = false;
+    std::string baseline_file;                         // "-" = stdin
     bool linear = false;
     bool talkless = true;
     int cuda_device = 0;                               // new: where the FFT worker runs

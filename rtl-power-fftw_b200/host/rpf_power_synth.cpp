@@ -2,6 +2,7 @@
 // for ONE hop, fed by the synthetic source instead of an RTL-SDR dongle:
 //   Plan -> Datastore -> Acquisition::run -> print_summary -> write_data -> histogram.
 // usage: rpf_power_synth N repeats [window:0|1] [seed] [mode] [buf_length|0] [buffers] [linear:0|1] [device]
+//                        [-w window_file|-] [-B baseline_file|-] [--dump-aux]
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
@@ -27,11 +28,28 @@ int main(int argc, char **argv)
         if (argc > 7) params.buffers = std::atoi(argv[7]);
         params.linear = argc > 8 && std::atoi(argv[8]) != 0;
         if (argc > 9) params.cuda_device = std::atoi(argv[9]);
+        bool dump_aux = false;
+        for (int i = 10; i < argc; i++) {                          // optional: -w FILE  -B FILE  --dump-aux
+            std::string a = argv[i];
+            if (a == "-w" && i + 1 < argc) { params.window = true; params.window_file = argv[++i]; }
+            else if (a == "-B" && i + 1 < argc) { params.baseline = true; params.baseline_file = argv[++i]; }
+            else if (a == "--dump-aux") dump_aux = true;
+        }
         if (params.buf_length % base_buf != 0)                     // src/params.cxx:166-170
             params.buf_length = (int)(std::floor((double)params.buf_length / base_buf + 0.5) * base_buf);
 
         AuxData aux;
-        if (params.window) {                                       // Hann, as BASELINE config 3
+        if (!params.window_file.empty() || !params.baseline_file.empty()) {
+            aux = AuxData(params);                                  // text files / stdin, as the reference's AuxData
+            if (dump_aux) {                                         // parser check, no GPU involved
+                std::cout.precision(17);
+                std::cout << "window " << aux.window_values.size() << std::endl;
+                for (float v : aux.window_values) std::cout << v << std::endl;
+                std::cout << "baseline " << aux.baseline_values.size() << std::endl;
+                for (double v : aux.baseline_values) std::cout << v << std::endl;
+                return (int)ReturnValue::Success;
+            }
+        } else if (params.window) {                                // Hann, as BASELINE config 3
             aux.window_values.resize(params.N);
             for (int n = 0; n < params.N; n++)
                 aux.window_values[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / params.N));

@@ -97,3 +97,34 @@ def test_shard_ranges_cover_and_are_spectrum_aligned():
         assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
         assert max(b - a for a, b in ranges) - min(b - a for a, b in ranges) <= 1
     assert sh.shard_byte_range(4096, 80000000, 1, 8) == (2 * 4096 * 10000000, 2 * 4096 * 20000000)
+
+
+def test_auxdata_text_reader(tmp_path):
+    """Window / baseline text files (src/acquisition.cxx:32-156): last number per line, '#' comments,
+    blank / non-numeric lines skipped, exactly N values or InvalidInput (exit code 5)."""
+    exe = os.path.join(ROOT, "rtl-power-fftw_b200", "host", "rpf_power_synth")
+    N = 8
+    w = tmp_path / "win.txt"
+    w.write_text("# window\n\n  # indented comment\n0.0\n1 0.25\n2 3 0.5\nabc\n0.75\n1.0\n0.75e0\n 5e-1\n0.25\n")
+    b = tmp_path / "base.txt"
+    b.write_text("".join("%d %.17g\n" % (i, -1.5 + i * 0.1234567890123) for i in range(N)))
+    args = [exe, str(N), "1", "0", "1", "1", "0", "5", "0", "0"]
+    r = subprocess.run(args + ["-w", str(w), "-B", str(b), "--dump-aux"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.split()
+    assert lines[0] == "window" and int(lines[1]) == N
+    win = np.array(lines[2:2 + N], dtype=np.float64)
+    assert np.array_equal(win.astype(np.float32), np.array([0, .25, .5, .75, 1, .75, .5, .25], np.float32))
+    assert lines[2 + N] == "baseline" and int(lines[3 + N]) == N
+    base = np.array(lines[4 + N:4 + 2 * N], dtype=np.float64)
+    assert np.array_equal(base, np.array([-1.5 + i * 0.1234567890123 for i in range(N)]))
+    # both from stdin: first N -> window, next N -> baseline
+    both = "".join("%g\n" % v for v in list(range(N)) + [10 + v for v in range(N)])
+    r = subprocess.run(args + ["-w", "-", "-B", "-", "--dump-aux"], input=both, capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split()[2:2 + N] == [str(v) for v in range(N)]
+    # wrong count / missing file -> ReturnValue::InvalidInput
+    w.write_text("1\n2\n3\n")
+    r = subprocess.run(args + ["-w", str(w), "--dump-aux"], capture_output=True, text=True)
+    assert r.returncode == 5 and "Expected 8 values, found 3" in r.stderr
+    r = subprocess.run(args + ["-B", str(tmp_path / "nope"), "--dump-aux"], capture_output=True, text=True)
+    assert r.returncode == 5 and "Could not open" in r.stderr
