@@ -151,9 +151,11 @@ template <> struct Dft<16> {
 };
 
 // Radix-16 in two halves, so that a caller can issue independent memory operations in between
-// (software pipelining).  dft16_first: 4 radix-4 butterflies over n1 (x[4 n1 + n0]) + the internal
-// W_16^{n0 k0} twiddles, result a[n0][k0] left in x[4 k0 + n0].  dft16_second: 4 radix-4 butterflies
-// over n0, result X[k0 + 4 k1] in natural order.  dft16_first followed by dft16_second == Dft<16>::run.
+// (software pipelining).  dft16_first: 4 radix-4 butterflies over n1 (x[4 n1 + n0]), result
+// a[n0][k0] left in x[4 k0 + n0] -- WITHOUT the internal W_16^{n0 k0} twiddles.  dft16_second applies
+// those twiddles fused into its radix-4 butterflies (FMA form: s0 = a0 + w2 a2 is two FFMA2,
+// s1 = 2 a0 - s0 one more; 43 packed ops instead of 48) and leaves X[k0 + 4 k1] in natural order.
+// dft16_first followed by dft16_second == Dft<16>::run up to rounding.
 __device__ __forceinline__ void dft16_first(c32 *x)
 {
     c32 a[16];
@@ -164,23 +166,49 @@ __device__ __forceinline__ void dft16_first(c32 *x)
 #pragma unroll
         for (int k0 = 0; k0 < 4; k0++) a[4 * k0 + n0] = col[k0];
     }
-    // a[4 k0 + n0] *= W_16^{n0 k0}
-    a[4 * 1 + 1] = mul_w16<1>(a[4 * 1 + 1]); a[4 * 1 + 2] = mul_w16<2>(a[4 * 1 + 2]); a[4 * 1 + 3] = mul_w16<3>(a[4 * 1 + 3]);
-    a[4 * 2 + 1] = mul_w16<2>(a[4 * 2 + 1]); a[4 * 2 + 2] = mul_w16<4>(a[4 * 2 + 2]); a[4 * 2 + 3] = mul_w16<6>(a[4 * 2 + 3]);
-    a[4 * 3 + 1] = mul_w16<3>(a[4 * 3 + 1]); a[4 * 3 + 2] = mul_w16<6>(a[4 * 3 + 2]); a[4 * 3 + 3] = mul_w16<9>(a[4 * 3 + 3]);
 #pragma unroll
     for (int i = 0; i < 16; i++) x[i] = a[i];
+}
+// a + w b with w = W_16^J (compile-time): two FFMA2
+template <int J>
+__device__ __forceinline__ c32 fma_w16(c32 a, c32 b)
+{
+    constexpr int j = ((J % 16) + 16) % 16;
+    constexpr float wr = rpf_cos16(j), wi = -rpf_cos16((j + 12) % 16);
+    const c32 t = __ffma2_rn(b, make_float2(wr, wr), a);
+    return __ffma2_rn(make_float2(b.y, b.x), make_float2(-wi, wi), t);
+}
+// 2 a - s
+__device__ __forceinline__ c32 twice_minus(c32 a, c32 s) { return __ffma2_rn(a, make_float2(2.0f, 2.0f), make_float2(-s.x, -s.y)); }
+
+// radix-4 over (a0, w1 a1, w2 a2, w3 a3) with w_q = W_16^{q K0}
+template <int K0>
+__device__ __forceinline__ void radix4_tw(c32 a0, c32 a1, c32 a2, c32 a3, c32 &y0, c32 &y1, c32 &y2, c32 &y3)
+{
+    c32 s0, s1, s2, s3;
+    if (K0 == 0) {
+        s0 = cadd(a0, a2); s1 = csub(a0, a2); s2 = cadd(a1, a3); s3 = csub(a1, a3);
+    } else {
+        if ((2 * K0) % 16 == 4) {            // w2 = -i
+            s0 = cadd_mi(a0, a2); s1 = cadd_pi(a0, a2);
+        } else {
+            s0 = fma_w16<2 * K0>(a0, a2); s1 = twice_minus(a0, s0);
+        }
+        const c32 p1 = mul_w16<K0>(a1);
+        s2 = fma_w16<3 * K0>(p1, a3); s3 = twice_minus(p1, s2);
+    }
+    y0 = cadd(s0, s2);
+    y1 = cadd_mi(s1, s3);
+    y2 = csub(s0, s2);
+    y3 = cadd_pi(s1, s3);
 }
 __device__ __forceinline__ void dft16_second(c32 *x)
 {
     c32 y[16];
-#pragma unroll
-    for (int k0 = 0; k0 < 4; k0++) {
-        c32 row[4] = {x[4 * k0], x[4 * k0 + 1], x[4 * k0 + 2], x[4 * k0 + 3]};
-        Dft<4>::run(row);
-#pragma unroll
-        for (int k1 = 0; k1 < 4; k1++) y[k0 + 4 * k1] = row[k1];
-    }
+    radix4_tw<0>(x[0], x[1], x[2], x[3], y[0], y[4], y[8], y[12]);
+    radix4_tw<1>(x[4], x[5], x[6], x[7], y[1], y[5], y[9], y[13]);
+    radix4_tw<2>(x[8], x[9], x[10], x[11], y[2], y[6], y[10], y[14]);
+    radix4_tw<3>(x[12], x[13], x[14], x[15], y[3], y[7], y[11], y[15]);
 #pragma unroll
     for (int i = 0; i < 16; i++) x[i] = y[i];
 }
