@@ -146,8 +146,10 @@ __device__ __forceinline__ void dft_composite(c32 *x)
 template <> struct Dft<8> {
     static __device__ __forceinline__ void run(c32 *x) { dft_composite<2, 4>(x); }
 };
-template <> struct Dft<16> {
-    static __device__ __forceinline__ void run(c32 *x) { dft_composite<4, 4>(x); }
+__device__ __forceinline__ void dft16_first(c32 *x);
+__device__ __forceinline__ void dft16_second(c32 *x);
+template <> struct Dft<16> {   // two radix-4 layers, internal twiddles in FMA form (75 packed ops)
+    static __device__ __forceinline__ void run(c32 *x) { dft16_first(x); dft16_second(x); }
 };
 
 // Radix-16 in two halves, so that a caller can issue independent memory operations in between

@@ -66,9 +66,9 @@ struct Geo {
     static_assert(R1 * R2 * R3 == N, "radix schedule");
 };
 
-template <int N, bool WINDOW, bool SRC_C32>
+template <int N, bool WINDOW>
 __global__ void __launch_bounds__(kBlock, RPF_MINBLOCKS)
-fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx, int64_t nspec, int M,
+fused3_kernel(const uint8_t *__restrict__ bytes, int64_t nspec,
               const float2 *__restrict__ twiddle, const float *__restrict__ window, double *__restrict__ rows)
 {
     using g = Geo<N>;
@@ -88,7 +88,7 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
     c32 *s2 = S2 + (size_t)grp * g::S2_ELEMS;
 
     // ---- work range (CTA iterations; one iteration = G consecutive spectra) --
-    const int64_t nitems = SRC_C32 ? nspec * (int64_t)M : nspec;     // spectra-sized work items
+    const int64_t nitems = nspec;
     const int64_t niter = (nitems + G - 1) / G;
     const int64_t it0 = (niter * (int64_t)blockIdx.x) / gridDim.x;
     const int nit = (int)((niter * (int64_t)(blockIdx.x + 1)) / gridDim.x - it0);   // < 2^31 per CTA
@@ -126,9 +126,8 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
 #pragma unroll
         for (int k = 0; k < R3; k++) acc[c][k] = 0.0f;
 
-    const int64_t rowlen = (int64_t)N * M;
+    const int64_t rowlen = N;
     double *row = rows + ((size_t)blockIdx.x * G + grp) * (size_t)rowlen;
-    int kouter = 0;                     // four-step: which outer bin this CTA is accumulating
 
     auto flush = [&]() {
 #pragma unroll
@@ -138,8 +137,7 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
 #pragma unroll
             for (int k3 = 0; k3 < R3; k3++) {
                 const int k = k1 + R1 * k2 + R1 * R2 * k3;                 // FFT output index
-                const int64_t bin = (int64_t)kouter + (int64_t)M * k;      // (four-step: k1' + M k)
-                const int64_t out = (bin + (rowlen >> 1)) & (rowlen - 1);  // fftshift == (-1)^n trick
+                const int64_t out = (k + (rowlen >> 1)) & (rowlen - 1);    // fftshift == (-1)^n trick
                 row[out] += (double)acc[c][k3];
                 acc[c][k3] = 0.0f;
             }
@@ -147,7 +145,7 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
     };
 
     // ---- TMA ring ------------------------------------------------------------
-    const uint8_t *cta_bytes = SRC_C32 ? nullptr : bytes + (size_t)it0 * kIterBytes;
+    const uint8_t *cta_bytes = bytes + (size_t)it0 * kIterBytes;
     auto issue = [&](int j) {           // called by thread 0 only
         const int slot = j % kStages;
         const int64_t left = nitems - (it0 + j) * G;
@@ -158,36 +156,24 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
         tma_load_1d(smem_u32(ring + (size_t)slot * kIterBytes), cta_bytes + (size_t)j * kIterBytes, nbytes, bar);
     };
     if (tid == 0) {
-        if (!SRC_C32) {
 #pragma unroll
-            for (int s = 0; s < kStages; s++) mbar_init(smem_u32(&bars[s]), 1);
-        }
+        for (int s = 0; s < kStages; s++) mbar_init(smem_u32(&bars[s]), 1);
         mbar_init(smem_u32(&bars[kStages]), kBlock / 32);   // "S1 has been read" -- one arrival per warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (!SRC_C32 && tid == 0)
+    if (tid == 0)
         for (int s = 0; s < kStages; s++)
             if (s < nit) issue(s);
     const uint32_t bar_s1free = smem_u32(&bars[kStages]);
 
     int since_flush = 0;
     for (int j = 0; j < nit; j++) {
-        const bool valid = (G == 1 && !SRC_C32) ? true : (j < jvalid);
+        const bool valid = (G == 1) ? true : (j < jvalid);
         c32 v[16];
 
         // ================= pass 1: load + radix-R1 over the high digit =========
-        if (SRC_C32) {
-            const int64_t item = (it0 + j) * G + grp;
-            const int ko = (int)(item / nspec);
-            if (ko != kouter) { flush(); kouter = ko; since_flush = 0; }
-            const int64_t spec = item - (int64_t)ko * nspec;
-            const float2 *src = cplx + ((size_t)spec * M + ko) * (size_t)N;
-#pragma unroll
-            for (int c = 0; c < C1; c++)
-#pragma unroll
-                for (int n1 = 0; n1 < R1; n1++) v[c * R1 + n1] = __ldg(&src[n1 * NC1 + tau + T * c]);
-        } else {
+        {
             const int slot = j % kStages;
             mbar_wait(smem_u32(&bars[slot]), (uint32_t)((j / kStages) & 1));
             const uint8_t *raw = ring + (size_t)slot * kIterBytes + (size_t)grp * 2 * N;
@@ -207,7 +193,7 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
 #pragma unroll
         for (int c = 0; c < C1; c++) {
             Dft<R1>::run(&v[c * R1]);
-            if (!SRC_C32 && !WINDOW)   // remove the R1 * (32768+127) left in output 0 -- exact
+            if (!WINDOW)   // remove the R1 * (32768+127) left in output 0 -- exact
                 v[c * R1] = __fadd2_rn(v[c * R1], make_float2(-(float)R1 * kBias, -(float)R1 * kBias));
             const int t = tau + T * c;
 #pragma unroll
@@ -219,7 +205,7 @@ fused3_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx
             for (int k1 = 0; k1 < R1; k1++) s1[k1 * P1 + t] = v[c * R1 + k1];
         }
         __syncthreads();   // S1 complete; ring slot consumed
-        if (!SRC_C32 && tid == 0 && j + kStages < nit) issue(j + kStages);
+        if (tid == 0 && j + kStages < nit) issue(j + kStages);
 
         // ================= pass 2 ==============================================
 #pragma unroll
@@ -275,18 +261,13 @@ template <int N>
 cudaError_t launch_n(const RpfLaunch &L)
 {
     using g = Geo<N>;
-    const bool c32src = L.cplx != nullptr;
-    const bool win = L.window != nullptr && !c32src;   // four-step applies the window in the outer pass
-    const int64_t nitems = c32src ? L.nspec * L.M : L.nspec;
-    const int64_t niter = (nitems + g::G - 1) / g::G;
+    const int64_t niter = (L.nspec + g::G - 1) / g::G;
     if (niter <= 0) return cudaSuccess;
     dim3 grid((unsigned)(niter < L.grid ? niter : L.grid)), block(kBlock);
-    if (c32src)
-        fused3_kernel<N, false, true><<<grid, block, g::SMEM, L.stream>>>(nullptr, L.cplx, L.nspec, L.M, L.twiddle, nullptr, L.rows);
-    else if (win)
-        fused3_kernel<N, true, false><<<grid, block, g::SMEM, L.stream>>>(L.bytes, nullptr, L.nspec, 1, L.twiddle, L.window, L.rows);
+    if (L.window)
+        fused3_kernel<N, true><<<grid, block, g::SMEM, L.stream>>>(L.bytes, L.nspec, L.twiddle, L.window, L.rows);
     else
-        fused3_kernel<N, false, false><<<grid, block, g::SMEM, L.stream>>>(L.bytes, nullptr, L.nspec, 1, L.twiddle, nullptr, L.rows);
+        fused3_kernel<N, false><<<grid, block, g::SMEM, L.stream>>>(L.bytes, L.nspec, L.twiddle, nullptr, L.rows);
     return cudaGetLastError();
 }
 
@@ -294,13 +275,9 @@ template <int N>
 cudaError_t configure_n()
 {
     using g = Geo<N>;
-    cudaError_t e;
-    e = cudaFuncSetAttribute(fused3_kernel<N, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(fused3_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g::SMEM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fused3_kernel<N, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g::SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fused3_kernel<N, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g::SMEM);
-    return e;
+    return cudaFuncSetAttribute(fused3_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g::SMEM);
 }
 
 }  // namespace

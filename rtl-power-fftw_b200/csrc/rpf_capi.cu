@@ -34,9 +34,7 @@ struct rpf_ctx {
     int64_t rowlen = 0;               // doubles per private accumulator row
     size_t spectrum_bytes = 0;        // 2N
     bool has_window = false;
-    bool use4096 = false;             // dedicated N=4096 kernel (also the four-step inner transform)
-    bool usepipe = false;             // N=4096 from bytes: two-stream software-pipelined kernel
-    bool usepp = false;               // N=4096 from bytes: ping-pong warp-group kernel
+    bool usepipe = false;             // N=4096 (and the four-step inner transform): pipe4096_kernel
 
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[kNumStage] = {}, ev_consumed[kNumStage] = {};
@@ -118,8 +116,7 @@ int launch_spectra(rpf_ctx *c, const uint8_t *src, int64_t nspec)
     L.twiddle = c->d_twiddle; L.window = c->d_window; L.rows = c->d_rows;
     L.grid = c->grid; L.stream = c->stream;
     if (c->plan == PLAN_FUSED3) {
-        CU(c, c->usepp ? rpf_launch_pingpong4096(L) : c->usepipe ? rpf_launch_pipe4096(L)
-               : c->use4096 ? rpf_launch_fused4096(L) : rpf_launch_fused3(c->N, L));
+        CU(c, c->usepipe ? rpf_launch_pipe4096(L) : rpf_launch_fused3(c->N, L));
         c->launches++;
     } else if (c->plan == PLAN_SMALL) {
         CU(c, rpf_launch_small(c->N, L));
@@ -186,21 +183,17 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             CU(c, cudaHostAlloc((void **)&c->h_carry[i], c->spectrum_bytes, cudaHostAllocDefault));
         }
         int inner = N;
-        // development A/B switches only: RPF_B200_KERNEL=generic|fused4096 selects an older N=4096 kernel
+        // development A/B switch only: RPF_B200_KERNEL=generic runs N=4096 on the generic 3-pass kernel
         const char *kname = getenv("RPF_B200_KERNEL");
         const bool generic = kname && !strcmp(kname, "generic");
-        const bool lockstep = kname && !strcmp(kname, "fused4096");
-        const bool pingpong = kname && !strcmp(kname, "pingpong");
         if (!is_pow2(N)) {
             c->plan = PLAN_DIRECT; c->groups = 1; c->grid = 4 * sms;
             CU(c, rpf_direct_dft_configure());
         } else if (rpf_fused3_supported(N)) {
             c->plan = PLAN_FUSED3;
-            c->usepp = (N == kInnerN) && pingpong;
-            c->usepipe = (N == kInnerN) && !generic && !lockstep && !pingpong;
-            c->use4096 = (N == kInnerN) && lockstep;
-            c->groups = c->usepipe ? 1 : (c->use4096 || c->usepp) ? 2 : rpf_fused3_groups(N);
-            c->grid = (c->usepipe || c->use4096 || c->usepp) ? sms : 2 * sms;
+            c->usepipe = (N == kInnerN) && !generic;
+            c->groups = c->usepipe ? 1 : rpf_fused3_groups(N);
+            c->grid = c->usepipe ? sms : 2 * sms;
         } else if (N <= 256) {
             c->plan = PLAN_SMALL; c->groups = 1; c->grid = 8 * sms;
         } else {
@@ -218,9 +211,7 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
         }
         if (c->plan != PLAN_SMALL && c->plan != PLAN_DIRECT) {
             CU(c, rpf_fused3_configure());
-            CU(c, rpf_fused4096_configure());
             CU(c, rpf_pipe4096_configure());
-            CU(c, rpf_pingpong4096_configure());
         }
         std::vector<float2> tw;
         fill_twiddle(tw, inner);

@@ -22,18 +22,9 @@ int rpf_fused3_groups(int N);          // spectra per CTA iteration (G)
 bool rpf_fused3_supported(int N);
 cudaError_t rpf_fused3_configure();    // opt-in shared memory attributes (once per device)
 
-// N = 4096 specialisation (512-thread CTAs, two spectra per iteration, warp-uniform pass-2 twiddles).
-cudaError_t rpf_launch_fused4096(const RpfLaunch &L);
-cudaError_t rpf_fused4096_configure();
-int rpf_fused4096_groups();
-
 // N = 4096, two-stream software pipeline (256-thread CTAs, two spectra per thread): the product path.
 cudaError_t rpf_launch_pipe4096(const RpfLaunch &L);
 cudaError_t rpf_pipe4096_configure();
-
-// N = 4096, two warp-groups per CTA alternating on the FP32 pipe (512-thread CTAs).
-cudaError_t rpf_launch_pingpong4096(const RpfLaunch &L);
-cudaError_t rpf_pingpong4096_configure();
 
 // Generic power-of-two N in [2,256]: shared-memory radix-2 Stockham.
 cudaError_t rpf_launch_small(int N, const RpfLaunch &L);
