@@ -79,7 +79,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -298,7 +298,6 @@ def main():
     ev[1].record()
     torch.cuda.synchronize()
     barrier()
-    clocks = sampler.stop() if sampler else None
     launches = ctx.kernel_launches - l0
     ms_total = ev[0].elapsed_time(ev[1])
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
@@ -355,6 +354,7 @@ def main():
                "sample": "%d spectra per GPU per step from a %d MiB pinned host ring, rpf_push in %d MiB chunks, "
                          "host wall clock (max over ranks)" % (e2e_spec, E2E_RING_BYTES >> 20, E2E_CHUNK >> 20)}
         pkg.lib().rpf_host_free(ring_ptr)
+    clocks = sampler.stop() if sampler else None      # covers the device-timed and the e2e regions
     ctx.close()
 
     if rank == 0:

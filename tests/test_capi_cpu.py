@@ -128,3 +128,23 @@ def test_auxdata_text_reader(tmp_path):
     assert r.returncode == 5 and "Expected 8 values, found 3" in r.stderr
     r = subprocess.run(args + ["-B", str(tmp_path / "nope"), "--dump-aux"], capture_output=True, text=True)
     assert r.returncode == 5 and "Could not open" in r.stderr
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with
+    the contract's keys; it times the reference's own worker loop (oracle/_ref) on the host cores."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference"
+    if "unavailable" in line:
+        return
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["unit"] == "Msamples/s" and line["value"] > 1.0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
