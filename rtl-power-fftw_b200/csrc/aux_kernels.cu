@@ -73,34 +73,47 @@ small_kernel(int N, const uint8_t *__restrict__ bytes, int64_t nspec, const floa
 }
 
 // ---------------------------------------------------------------------------
-// Four-step outer pass.  n = n1*4096 + m, k = k1 + M*k'.  One thread per (spec, m).
+// Four-step outer pass.  n = n1*4096 + m, k = k1 + M*k'.  Persistent threads: the grid is a whole
+// number of 4096-thread "rows", so a thread keeps the same m for every spectrum it visits and its
+// M-1 twiddles W_N^{m k1} (and window values) live in registers; per spectrum it reads M samples
+// (stride 8 KiB, 64 contiguous bytes per warp), runs the radix-M butterfly and writes M coalesced
+// complex64 values.
 // ---------------------------------------------------------------------------
-template <int M>
+template <int M, bool WINDOW>
 __global__ void __launch_bounds__(256)
 fourstep_outer_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__restrict__ twbig,
                       const float *__restrict__ window, float2 *__restrict__ scratch)
 {
     constexpr int NI = 4096;
     constexpr int NT = M * NI;
-    const int64_t total = nspec * NI;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t spec = idx / NI;
-        const int m = (int)(idx - spec * NI);
-        const uint8_t *raw = bytes + (size_t)spec * 2 * NT;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = (int)(gtid & (NI - 1));
+    const int64_t spec0 = gtid / NI, stride = ((int64_t)gridDim.x * blockDim.x) / NI;   // whole rows only
+    float2 tw[M];
+    float win[WINDOW ? M : 1];
+#pragma unroll
+    for (int k1 = 1; k1 < M; k1++) tw[k1] = __ldg(&twbig[(m * k1) & (NT - 1)]);
+    if (WINDOW) {
+#pragma unroll
+        for (int n1 = 0; n1 < M; n1++) win[n1] = window[n1 * NI + m];
+    }
+    for (int64_t spec = spec0; spec < nspec; spec += stride) {
+        const uint8_t *raw = bytes + (size_t)spec * 2 * NT + 2 * m;
+        uint32_t r[M];
+#pragma unroll
+        for (int n1 = 0; n1 < M; n1++) r[n1] = *reinterpret_cast<const uint16_t *>(raw + (size_t)n1 * 2 * NI);
         c32 v[M];
 #pragma unroll
         for (int n1 = 0; n1 < M; n1++) {
-            const uint32_t r = *reinterpret_cast<const uint16_t *>(raw + 2 * ((size_t)n1 * NI + m));
-            float re = (float)(r & 255u) - 127.0f, im = (float)(r >> 8) - 127.0f;
-            if (window) { const float w = window[n1 * NI + m]; re *= w; im *= w; }
+            float re = (float)(r[n1] & 255u) - 127.0f, im = (float)(r[n1] >> 8) - 127.0f;   // src/datastore.cxx:74-75
+            if (WINDOW) { re *= win[n1]; im *= win[n1]; }                                     // :76-77
             v[n1] = make_float2(re, im);
         }
         Dft<M>::run(v);
         float2 *dst = scratch + (size_t)spec * NT + m;
         dst[0] = v[0];
 #pragma unroll
-        for (int k1 = 1; k1 < M; k1++) dst[(size_t)k1 * NI] = cmul(v[k1], __ldg(&twbig[(m * k1) & (NT - 1)]));
+        for (int k1 = 1; k1 < M; k1++) dst[(size_t)k1 * NI] = cmul(v[k1], tw[k1]);
     }
 }
 
@@ -173,20 +186,31 @@ cudaError_t rpf_launch_small(int N, const RpfLaunch &L)
     return cudaGetLastError();
 }
 
+template <int M>
+static cudaError_t launch_outer(const uint8_t *bytes, int64_t nspec, const float2 *twbig, const float *window,
+                                float2 *scratch, cudaStream_t stream)
+{
+    // whole 4096-thread rows: 16 blocks of 256 per row, about 16 rows' worth of blocks per wave
+    int64_t rows = nspec < 148 ? nspec : 148;
+    const int blocks = (int)(rows * 16);
+    if (window)
+        fourstep_outer_kernel<M, true><<<blocks, 256, 0, stream>>>(bytes, nspec, twbig, window, scratch);
+    else
+        fourstep_outer_kernel<M, false><<<blocks, 256, 0, stream>>>(bytes, nspec, twbig, nullptr, scratch);
+    return cudaGetLastError();
+}
+
 cudaError_t rpf_launch_fourstep_outer(int M, const uint8_t *bytes, int64_t nspec, const float2 *twbig,
                                       const float *window, float2 *scratch, cudaStream_t stream)
 {
-    const int64_t total = nspec * 4096;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (nspec <= 0) return cudaSuccess;
     switch (M) {
-        case 2: fourstep_outer_kernel<2><<<blocks, 256, 0, stream>>>(bytes, nspec, twbig, window, scratch); break;
-        case 4: fourstep_outer_kernel<4><<<blocks, 256, 0, stream>>>(bytes, nspec, twbig, window, scratch); break;
-        case 8: fourstep_outer_kernel<8><<<blocks, 256, 0, stream>>>(bytes, nspec, twbig, window, scratch); break;
-        case 16: fourstep_outer_kernel<16><<<blocks, 256, 0, stream>>>(bytes, nspec, twbig, window, scratch); break;
+        case 2: return launch_outer<2>(bytes, nspec, twbig, window, scratch, stream);
+        case 4: return launch_outer<4>(bytes, nspec, twbig, window, scratch, stream);
+        case 8: return launch_outer<8>(bytes, nspec, twbig, window, scratch, stream);
+        case 16: return launch_outer<16>(bytes, nspec, twbig, window, scratch, stream);
         default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 cudaError_t rpf_launch_reduce_rows(const double *rows, int nrows, int64_t rowlen, double *pwr, cudaStream_t stream)
