@@ -348,6 +348,9 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
+        # the e2e result must be a real spectrum too (Parseval: mean bin power ~ spectra * N * 2 sigma^2)
+        e2e_expect = world * e2e_spec * N_BINS * (2 * 30.0 ** 2)
+        assert np.all(np.isfinite(host_pwr)) and 0.5 * e2e_expect < host_pwr.mean() < 1.5 * e2e_expect, (host_pwr.mean(), e2e_expect)
         e2e = {"value": world * e2e_spec * N_BINS * e2e_steps / dt / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": world * E2E_PASSES * E2E_RING_BYTES, "d2h_bytes_per_step": world * N_BINS * 8,
                "steps": e2e_steps,
