@@ -29,11 +29,6 @@ constexpr int kThreads = 256;
 #define RPF_PIPE_STAGES 3
 #endif
 constexpr int kStagesP = RPF_PIPE_STAGES;         // TMA ring depth per stream
-// Timing experiments only (wrong results): RPF_ABL & 2 drops the exchange loads/stores (protocol kept),
-// RPF_ABL & 4 drops the mbarrier waits on the exchange barriers as well, RPF_ABL & 8 drops the unpack PRMTs.
-#ifndef RPF_ABL
-#define RPF_ABL 0
-#endif
 constexpr int kSpecBytes = 2 * kN;                // 8 KiB
 constexpr int kFlushPairs = 64;                   // flush every 64 iterations = 128 spectra
 constexpr int kHdrP = 128;
@@ -53,14 +48,12 @@ __device__ __forceinline__ void lds16x16(uint32_t base, uint32_t (&raw)[16])
 template <int STRIDE>
 __device__ __forceinline__ void lds64x16(uint32_t base, c32 (&v)[16])
 {
-    if (RPF_ABL & 2) return;
 #pragma unroll
     for (int i = 0; i < 16; i++)
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[i].x), "=f"(v[i].y) : "r"(base + i * STRIDE));
 }
 __device__ __forceinline__ void sts_s1(uint32_t base, const c32 (&v)[16])
 {
-    if (RPF_ABL & 2) return;
 #pragma unroll
     for (int u = 0; u < 8; u++)
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base ^ (u << 4)), "f"(v[2 * u].x), "f"(v[2 * u].y),
@@ -68,7 +61,6 @@ __device__ __forceinline__ void sts_s1(uint32_t base, const c32 (&v)[16])
 }
 __device__ __forceinline__ void sts_s2(uint32_t base, const c32 (&v)[16])
 {
-    if (RPF_ABL & 2) return;
 #pragma unroll
     for (int k2 = 0; k2 < 16; k2++)
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(base + k2 * 2048), "f"(v[k2].x), "f"(v[k2].y) : "memory");
@@ -194,7 +186,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     auto unpack = [&](c32 (&v)[16]) {
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) {
-            c32 x = (RPF_ABL & 8) ? make_float2(__uint_as_float(raw[n1]), __uint_as_float(raw[n1] + 1u)) : unpack_biased(raw[n1]);
+            c32 x = unpack_biased(raw[n1]);
             if (WINDOW) {        // (u8 - 127.0f) * w, one rounding per rail: src/datastore.cxx:75-77
                 x = __fadd2_rn(x, make_float2(-kBias, -kBias));
                 x = __fmul2_rn(x, make_float2(win[n1], win[n1]));
@@ -251,7 +243,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         // ---- (B,1)  | prefetch S1[A] ----------------------------------------------------------
         if (!SRC_C32) unpack(vB);
         dft16_first(vB);
-        if (!(RPF_ABL & 4)) rd_wait(sm + 8 * bar_rd(0, 1), j);         // every warp has stored its (A,1) rows
+        rd_wait(sm + 8 * bar_rd(0, 1), j);         // every warp has stored its (A,1) rows
         if (tid == 0 && j + kStagesP < nit) issue(0, j + kStagesP);   // ... so A's ring slot is free
         lds64x16<2048>(s1_ld, vA);
         dft16_second(vB);
@@ -259,7 +251,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 
         // ---- (A,2)  | prefetch S1[B] ----------------------------------------------------------
         dft16_first(vA);
-        if (!(RPF_ABL & 4)) rd_wait(sm + 8 * bar_rd(1, 1), j);
+        rd_wait(sm + 8 * bar_rd(1, 1), j);
         if (tid == 0 && j + kStagesP < nit) issue(1, j + kStagesP);
         lds64x16<2048>(s1_ld + kStreamS, vB);
         dft16_second(vA);
@@ -267,14 +259,14 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 
         // ---- (B,2)  | prefetch S2[A] ----------------------------------------------------------
         dft16_first(vB);
-        if (!(RPF_ABL & 4)) rd_wait(sm + 8 * bar_rd(0, 2), j);
+        rd_wait(sm + 8 * bar_rd(0, 2), j);
         lds64x16<128>(s2_ld, vA);
         dft16_second(vB);
         post2(vB, 1);
 
         // ---- (A,3)  | prefetch S2[B] ----------------------------------------------------------
         dft16_first(vA);
-        if (!(RPF_ABL & 4)) rd_wait(sm + 8 * bar_rd(1, 2), j);
+        rd_wait(sm + 8 * bar_rd(1, 2), j);
         lds64x16<128>(s2_ld + kStreamS, vB);
         dft16_second(vA);
         power(vA);
