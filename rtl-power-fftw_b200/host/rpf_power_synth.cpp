@@ -2,7 +2,7 @@
 // for ONE hop, fed by the synthetic source instead of an RTL-SDR dongle:
 //   Plan -> Datastore -> Acquisition::run -> print_summary -> write_data -> histogram.
 // usage: rpf_power_synth N repeats [window:0|1] [seed] [mode] [buf_length|0] [buffers] [linear:0|1] [device]
-//                        [-w window_file|-] [-B baseline_file|-] [--dump-aux]
+//                        [-w window_file|-] [-B baseline_file|-] [--dump-aux] [--hops H]
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
@@ -29,11 +29,13 @@ int main(int argc, char **argv)
         params.linear = argc > 8 && std::atoi(argv[8]) != 0;
         if (argc > 9) params.cuda_device = std::atoi(argv[9]);
         bool dump_aux = false;
+        int hops = 1;                                              // acquisitions on ONE Datastore, a fresh worker each
         for (int i = 10; i < argc; i++) {                          // optional: -w FILE  -B FILE  --dump-aux
             std::string a = argv[i];
             if (a == "-w" && i + 1 < argc) { params.window = true; params.window_file = argv[++i]; }
             else if (a == "-B" && i + 1 < argc) { params.baseline = true; params.baseline_file = argv[++i]; }
             else if (a == "--dump-aux") dump_aux = true;
+            else if (a == "--hops" && i + 1 < argc) hops = std::atoi(argv[++i]);
         }
         if (params.buf_length % base_buf != 0)                     // src/params.cxx:166-170
             params.buf_length = (int)(std::floor((double)params.buf_length / base_buf + 0.5) * base_buf);
@@ -57,11 +59,14 @@ int main(int argc, char **argv)
         SyntheticSource source(seed, mode);
         Plan plan(params, params.sample_rate);
         Datastore data(params, aux.window_values);
-        Acquisition acquisition(params, aux, source, data, params.sample_rate, params.cfreq);
-        acquisition.run();
-        acquisition.print_summary();
-        acquisition.write_data(std::cout);
-        data.printQueueHistogram();
+        for (int hop = 0; hop < hops; hop++) {                     // the hop loop of src/rtl_power_fftw.cxx:132-205
+            source.rewind();                                       // same bytes every hop: outputs must repeat exactly
+            Acquisition acquisition(params, aux, source, data, params.sample_rate, params.cfreq);
+            acquisition.run();
+            acquisition.print_summary();
+            acquisition.write_data(std::cout);
+            data.printQueueHistogram();
+        }
         return (int)ReturnValue::Success;
     } catch (const RPFexception &e) {
         std::cerr << e.what() << std::endl;
