@@ -62,3 +62,32 @@ def test_one_hop_text_output(N, repeats, window, mode, buf, linear):
 def test_invalid_bins_exit_code():
     r = subprocess.run([EXE, "10000", "10"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 3 and "not supported" in r.stderr             # ReturnValue::InvalidArgument
+
+
+def test_datastore_reused_across_hops():
+    """One Datastore, several Acquisition::run() calls (a fresh worker thread per hop, reset per hop,
+    src/acquisition.cxx:252-256): identical input -> byte-identical output blocks; the queue histogram
+    keeps counting across hops as in the reference (it is never reset)."""
+    r = subprocess.run([EXE, "4096", "450", "0", "77", "1", "1638400", "5", "0", "0", "--hops", "3"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    blocks = [b for b in r.stdout.split("# rtl-power-fftw output") if b.strip()]
+    assert len(blocks) == 3 and blocks[0] == blocks[1] == blocks[2]
+    hist = [sum(int(x) for x in ln.split(":")[1].split()) for ln in r.stderr.splitlines()
+            if ln.startswith("Buffer queue histogram:")]
+    assert hist == [3, 6, 9]
+
+
+def test_results_are_run_to_run_deterministic():
+    """Private float64 rows + fixed-order reduction: the same push sequence gives bit-identical pwr."""
+    from rpf import Context
+    N, R = 4096, 3000
+    s = pkg.synth_fill_host(2 * N * R, 0, seed=31, mode=1)
+    outs = []
+    for _ in range(2):
+        with Context(N) as c:
+            c.reset(R)
+            for off in range(0, s.size, 1638400):
+                c.push(s[off:off + 1638400])
+            outs.append(c.finish()[0])
+    assert np.array_equal(outs[0], outs[1])
