@@ -171,6 +171,18 @@ __device__ __forceinline__ void dft16_first(c32 *x)
 #pragma unroll
     for (int i = 0; i < 16; i++) x[i] = a[i];
 }
+// columns [C0, C1) of dft16_first, in place (column n0 touches x[n0], x[4+n0], x[8+n0], x[12+n0] only)
+template <int C0, int C1>
+__device__ __forceinline__ void dft16_first_cols(c32 *x)
+{
+#pragma unroll
+    for (int n0 = C0; n0 < C1; n0++) {
+        c32 col[4] = {x[n0], x[4 + n0], x[8 + n0], x[12 + n0]};
+        Dft<4>::run(col);
+#pragma unroll
+        for (int k0 = 0; k0 < 4; k0++) x[4 * k0 + n0] = col[k0];
+    }
+}
 // a + w b with w = W_16^J (compile-time): two FFMA2
 template <int J>
 __device__ __forceinline__ c32 fma_w16(c32 a, c32 b)
@@ -204,13 +216,23 @@ __device__ __forceinline__ void radix4_tw(c32 a0, c32 a1, c32 a2, c32 a3, c32 &y
     y2 = csub(s0, s2);
     y3 = cadd_pi(s1, s3);
 }
-__device__ __forceinline__ void dft16_second(c32 *x)
+// dft16_second in two halves (a caller may put memory operations in between): y is scratch, the
+// result is in x after dft16_second_b.
+__device__ __forceinline__ void dft16_second_a(const c32 *x, c32 *y)
 {
-    c32 y[16];
     radix4_tw<0>(x[0], x[1], x[2], x[3], y[0], y[4], y[8], y[12]);
     radix4_tw<1>(x[4], x[5], x[6], x[7], y[1], y[5], y[9], y[13]);
+}
+__device__ __forceinline__ void dft16_second_b(c32 *x, c32 *y)
+{
     radix4_tw<2>(x[8], x[9], x[10], x[11], y[2], y[6], y[10], y[14]);
     radix4_tw<3>(x[12], x[13], x[14], x[15], y[3], y[7], y[11], y[15]);
 #pragma unroll
     for (int i = 0; i < 16; i++) x[i] = y[i];
+}
+__device__ __forceinline__ void dft16_second(c32 *x)
+{
+    c32 y[16];
+    dft16_second_a(x, y);
+    dft16_second_b(x, y);
 }

@@ -25,12 +25,15 @@ namespace {
 
 constexpr int kN = 4096;
 constexpr int kThreads = 256;
+#ifndef RPF_FLUSH_PAIRS
+#define RPF_FLUSH_PAIRS 64
+#endif
 #ifndef RPF_PIPE_STAGES
 #define RPF_PIPE_STAGES 2             // measured: 2 -> 587, 3 -> 578 (modulo-3 slot arithmetic), 4 -> 582 Gsamples/s
 #endif
 constexpr int kStagesP = RPF_PIPE_STAGES;         // TMA ring depth per stream
 constexpr int kSpecBytes = 2 * kN;                // 8 KiB
-constexpr int kFlushPairs = 64;                   // flush every 64 iterations = 128 spectra
+constexpr int kFlushPairs = RPF_FLUSH_PAIRS;      // flush every 64 iterations = 128 spectra
 constexpr int kHdrP = 128;
 constexpr int kS1Off = kHdrP + 2 * kStagesP * kSpecBytes;
 constexpr int kS2Off = kS1Off + 2 * kN * 8;
@@ -74,6 +77,22 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar)
 // place of the mbarrier: 15 % slower -- spinning warps burn issue slots and LSU bandwidth, whereas
 // try_wait parks the warp in hardware.)
 __device__ __forceinline__ void rd_wait(uint32_t bar, int j) { mbar_wait(bar, (uint32_t)(j & 1)); }
+
+// Stage scheduling knobs (measured on B200):
+//   RPF_LOADPOS  where, inside stage (Y,p), the wait for X's barrier and X's 16 loads sit:
+//                0 after the first half of Y's radix-16, 1 after three quarters, 2 after all of it,
+//                3 after the twiddle multiplications (just before Y's stores)
+//   RPF_PROBE    1: issue one try_wait at the top of the stage and branch on its answer at the wait point
+#ifndef RPF_LOADPOS
+#define RPF_LOADPOS 2
+#endif
+#ifndef RPF_PROBE
+#define RPF_PROBE 0
+#endif
+//   RPF_POWER2   1: |X|^2 accumulated as packed (re^2, im^2) pairs (one FFMA2 per bin instead of two FFMA)
+#ifndef RPF_POWER2
+#define RPF_POWER2 0
+#endif
 
 // SRC_C32 = false: spectra come as raw bytes (TMA ring), bins are flushed fftshifted.
 // SRC_C32 = true : the inner transform of the four-step path (N = M * 4096).  Input rows are complex64
@@ -123,9 +142,15 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) win[n1] = window[n1 * 256 + tid];
     }
+#if RPF_POWER2
+    c32 acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = make_float2(0.0f, 0.0f);
+#else
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) acc[k] = 0.0f;
+#endif
 
     // shared-memory addresses (stream B = +kSpecBytes in the ring, +32 KiB in S1/S2)
     const uint32_t ring = sm + kHdrP;                            // [stream][slot][8 KiB]
@@ -144,8 +169,13 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         for (int k3 = 0; k3 < 16; k3++) cur[k3] = row[(tid + 256 * k3 + kShift) & (kN - 1)];
 #pragma unroll
         for (int k3 = 0; k3 < 16; k3++) {
+#if RPF_POWER2
+            row[(tid + 256 * k3 + kShift) & (kN - 1)] = cur[k3] + ((double)acc[k3].x + (double)acc[k3].y);
+            acc[k3] = make_float2(0.0f, 0.0f);
+#else
             row[(tid + 256 * k3 + kShift) & (kN - 1)] = cur[k3] + (double)acc[k3];   // bin k = tid + 256 k3
             acc[k3] = 0.0f;
+#endif
         }
     };
     // four-step: row of complex64 for (stream s, local iteration j)
@@ -160,14 +190,18 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 
     // ---- TMA: one 8 KiB bulk copy per (stream, iteration) ------------------------------------
     const uint8_t *cta_bytes = SRC_C32 ? nullptr : bytes + (size_t)p0 * 2 * kSpecBytes;
+    // Ring slots are filled for A: iterations 0..nit (one past the end), B: 0..nit-1, so that every stage of
+    // every iteration waits and loads unconditionally; slots that have no spectrum of their own (B of an odd
+    // tail, A of iteration nit) re-read the last valid spectrum and their result is never accumulated.
+    const int last_valid = 2 * nit - 1 - (lastB_missing ? 1 : 0);
     auto issue = [&](int s, int j) {                 // thread 0 only; spectrum 2 (p0 + j) + s
         if (SRC_C32) return;
-        if (s == 1 && lastB_missing && j == nit - 1) return;
         const int slot = j % kStagesP;
         const uint32_t bar = sm + 8 * bar_full(s, slot);
+        const int idx = min(2 * j + s, last_valid);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar, kSpecBytes);
-        tma_load_1d(ring + (s * kStagesP + slot) * kSpecBytes, cta_bytes + ((size_t)2 * j + s) * kSpecBytes, kSpecBytes, bar);
+        tma_load_1d(ring + (s * kStagesP + slot) * kSpecBytes, cta_bytes + (size_t)idx * kSpecBytes, kSpecBytes, bar);
     };
     if (tid == 0) {
 #pragma unroll
@@ -178,7 +212,10 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     }
     __syncthreads();
     if (tid == 0)
-        for (int j = 0; j < kStagesP && j < nit; j++) { issue(0, j); issue(1, j); }
+        for (int j = 0; j < kStagesP; j++) {
+            if (j <= nit) issue(0, j);
+            if (j < nit) issue(1, j);
+        }
 
     c32 vA[16], vB[16];
     uint32_t raw[16];
@@ -194,22 +231,30 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
             v[n1] = x;
         }
     };
-    auto post1 = [&](c32 (&v)[16], int s) {          // bias fix, W_4096^{t k1}, store row t of S1[s], arrive
+    auto post1 = [&](c32 (&v)[16], int s, auto &&late) {   // bias fix, W_4096^{t k1}, store row t of S1[s], arrive
         if (!WINDOW && !SRC_C32) v[0] = __fadd2_rn(v[0], make_float2(-16.0f * kBias, -16.0f * kBias));
 #pragma unroll
         for (int k = 1; k < 16; k++) v[k] = cmul(v[k], tw1[k - 1]);
+        late();
         sts_s1(s1_st + s * kStreamS, v);
         warp_arrive(sm + 8 * bar_rd(s, 1));
     };
-    auto post2 = [&](c32 (&v)[16], int s) {          // W_256^{n3 k2}, store S2[s], arrive
+    auto post2 = [&](c32 (&v)[16], int s, auto &&late) {   // W_256^{n3 k2}, store S2[s], arrive
 #pragma unroll
         for (int k = 1; k < 16; k++) v[k] = cmul(v[k], tw2[k - 1]);
+        late();
         sts_s2(s2_st + s * kStreamS, v);
         warp_arrive(sm + 8 * bar_rd(s, 2));
     };
     auto power = [&](const c32 (&v)[16]) {
 #pragma unroll
-        for (int k3 = 0; k3 < 16; k3++) acc[k3] = fmaf(v[k3].x, v[k3].x, fmaf(v[k3].y, v[k3].y, acc[k3]));
+        for (int k3 = 0; k3 < 16; k3++) {
+#if RPF_POWER2
+            acc[k3] = __ffma2_rn(v[k3], v[k3], acc[k3]);
+#else
+            acc[k3] = fmaf(v[k3].x, v[k3].x, fmaf(v[k3].y, v[k3].y, acc[k3]));
+#endif
+        }
     };
 
     // prologue: input of stream A, iteration 0
@@ -226,62 +271,81 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         const uint32_t ph = (uint32_t)(j & 1);
         const bool haveB = !(lastB_missing && j == nit - 1);
 
+        // stage (Y,p): radix-16 on Y; `fetch` = wait for X's barrier + X's 16 loads, placed by RPF_LOADPOS
+        auto none = []() {};
+        auto radix = [&](c32 (&vY)[16], auto &&fetch) {
+            c32 y[16];
+            dft16_first(vY);
+            if (RPF_LOADPOS == 0) fetch();
+            dft16_second_a(vY, y);
+            if (RPF_LOADPOS == 1) fetch();
+            dft16_second_b(vY, y);
+            if (RPF_LOADPOS == 2) fetch();
+        };
+        const uint32_t rd = sm + 8 * bar_rd(0, 1);       // bar_rd(s, e) = rd + 8 (2 s + e - 1)
+        auto fetch_rawB = [&]() {
+            const uint32_t bar = sm + 8 * bar_full(1, slot), par = (uint32_t)((j / kStagesP) & 1);
+            mbar_wait(bar, par);
+            lds16x16(ring + (kStagesP + slot) * kSpecBytes + raw_off, raw);
+        };
+        auto fetch_s1A = [&]() {
+            mbar_wait(rd, ph);                               // every warp has stored its (A,1) rows ...
+            if (tid == 0 && j + kStagesP <= nit) issue(0, j + kStagesP);   // ... so A's ring slot is free
+            lds64x16<2048>(s1_ld, vA);
+        };
+        auto fetch_s1B = [&]() {
+            mbar_wait(rd + 16, ph);
+            if (tid == 0 && j + kStagesP < nit) issue(1, j + kStagesP);
+            lds64x16<2048>(s1_ld + kStreamS, vB);
+        };
+        auto fetch_s2A = [&]() { mbar_wait(rd + 8, ph); lds64x16<128>(s2_ld, vA); };
+        auto fetch_s2B = [&]() { mbar_wait(rd + 24, ph); lds64x16<128>(s2_ld + kStreamS, vB); };
+        auto fetch_rawA = [&]() {
+            const uint32_t bar = sm + 8 * bar_full(0, (j + 1) % kStagesP), par = (uint32_t)(((j + 1) / kStagesP) & 1);
+            mbar_wait(bar, par);
+            lds16x16(ring + ((j + 1) % kStagesP) * kSpecBytes + raw_off, raw);
+        };
+        constexpr bool kLate = RPF_LOADPOS == 3;
+
         // ---- (A,1)  | prefetch raw B ---------------------------------------------------------
-        if (!SRC_C32) unpack(vA);
-        dft16_first(vA);
-        if (haveB) {
-            if (SRC_C32) {
-                ldg16(crow(1, j), vB);
-            } else {
-                mbar_wait(sm + 8 * bar_full(1, slot), (uint32_t)((j / kStagesP) & 1));
-                lds16x16(ring + (kStagesP + slot) * kSpecBytes + raw_off, raw);
-            }
+        if (SRC_C32) {
+            dft16_first(vA);
+            if (haveB) ldg16(crow(1, j), vB);
+            dft16_second(vA);
+            post1(vA, 0, none);
+        } else {
+            unpack(vA);
+            radix(vA, fetch_rawB);
+            if (kLate) post1(vA, 0, fetch_rawB); else post1(vA, 0, none);
         }
-        dft16_second(vA);
-        post1(vA, 0);
 
         // ---- (B,1)  | prefetch S1[A] ----------------------------------------------------------
         if (!SRC_C32) unpack(vB);
-        dft16_first(vB);
-        rd_wait(sm + 8 * bar_rd(0, 1), j);         // every warp has stored its (A,1) rows
-        if (tid == 0 && j + kStagesP < nit) issue(0, j + kStagesP);   // ... so A's ring slot is free
-        lds64x16<2048>(s1_ld, vA);
-        dft16_second(vB);
-        post1(vB, 1);
+        radix(vB, fetch_s1A);
+        if (kLate) post1(vB, 1, fetch_s1A); else post1(vB, 1, none);
 
         // ---- (A,2)  | prefetch S1[B] ----------------------------------------------------------
-        dft16_first(vA);
-        rd_wait(sm + 8 * bar_rd(1, 1), j);
-        if (tid == 0 && j + kStagesP < nit) issue(1, j + kStagesP);
-        lds64x16<2048>(s1_ld + kStreamS, vB);
-        dft16_second(vA);
-        post2(vA, 0);
+        radix(vA, fetch_s1B);
+        if (kLate) post2(vA, 0, fetch_s1B); else post2(vA, 0, none);
 
         // ---- (B,2)  | prefetch S2[A] ----------------------------------------------------------
-        dft16_first(vB);
-        rd_wait(sm + 8 * bar_rd(0, 2), j);
-        lds64x16<128>(s2_ld, vA);
-        dft16_second(vB);
-        post2(vB, 1);
+        radix(vB, fetch_s2A);
+        if (kLate) post2(vB, 1, fetch_s2A); else post2(vB, 1, none);
 
         // ---- (A,3)  | prefetch S2[B] ----------------------------------------------------------
-        dft16_first(vA);
-        rd_wait(sm + 8 * bar_rd(1, 2), j);
-        lds64x16<128>(s2_ld + kStreamS, vB);
-        dft16_second(vA);
+        radix(vA, fetch_s2B);
+        if (kLate) fetch_s2B();
         power(vA);
 
         // ---- (B,3)  | prefetch raw A of the next iteration ------------------------------------
-        dft16_first(vB);
-        if (j + 1 < nit) {
-            if (SRC_C32) {
-                ldg16(crow(0, j + 1), vA);
-            } else {
-                mbar_wait(sm + 8 * bar_full(0, (j + 1) % kStagesP), (uint32_t)(((j + 1) / kStagesP) & 1));
-                lds16x16(ring + ((j + 1) % kStagesP) * kSpecBytes + raw_off, raw);
-            }
+        if (SRC_C32) {
+            dft16_first(vB);
+            if (j + 1 < nit) ldg16(crow(0, j + 1), vA);
+            dft16_second(vB);
+        } else {
+            radix(vB, fetch_rawA);
+            if (kLate) fetch_rawA();
         }
-        dft16_second(vB);
         if (haveB) power(vB);
 
         if (++since_flush == kFlushPairs) { flush(); since_flush = 0; }

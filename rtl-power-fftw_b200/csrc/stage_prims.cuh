@@ -35,6 +35,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     } while (!done);
 }
 
+// One try_wait (may suspend for the hardware time limit, returns whether the phase completed).
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done;
+}
+
 // Non-blocking probe (mbarrier.test_wait): issue it early, consume the answer later, and only fall
 // back to the (suspending, ~90-cycle) try_wait loop when the phase really has not completed yet.
 __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity)
