@@ -35,6 +35,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     } while (!done);
 }
 
+// elect.sync: true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // One try_wait (may suspend for the hardware time limit, returns whether the phase completed).
 __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity)
 {
