@@ -36,13 +36,21 @@ constexpr int kStagesP = RPF_PIPE_STAGES;         // TMA ring depth per stream
 constexpr int kSpecBytes = 2 * kN;                // 8 KiB
 constexpr int kFlushPairs = RPF_FLUSH_PAIRS;      // flush every 64 iterations = 128 spectra
 constexpr int kHdrP = 128;
-constexpr int kS1Off = kHdrP + 2 * kStagesP * kSpecBytes;
-constexpr int kS2Off = kS1Off + 2 * kN * 8;
-constexpr size_t kSmemP = (size_t)kS2Off + 2 * kN * 8;
-
-// barrier indices inside the header
-__device__ __forceinline__ constexpr int bar_full(int s, int slot) { return s * kStagesP + slot; }
-__device__ __forceinline__ constexpr int bar_rd(int s, int e) { return 2 * kStagesP + s * 2 + (e - 1); }
+// Shared-memory plan: header (mbarriers) | TMA ring [stream][slot] | S1 [stream][32 KiB] | S2 [stream][32 KiB].
+// Raw-byte spectra: kStagesP slots of 8 KiB per stream.  Complex64 rows (four-step inner transform): one slot
+// of 32 KiB per stream -- the slot is refilled as soon as every warp has stored its pass-1 rows, four
+// stages (~1.2 us) before the next row is needed, which covers the HBM latency.
+template <bool C32>
+struct Plan {
+    static constexpr int kStg = C32 ? 1 : kStagesP;            // ring depth per stream
+    static constexpr int kSlot = C32 ? kN * 8 : kSpecBytes;     // bytes per ring slot
+    static constexpr int kS1 = kHdrP + 2 * kStg * kSlot;
+    static constexpr int kS2 = kS1 + 2 * kN * 8;
+    static constexpr size_t kSmem = (size_t)kS2 + 2 * kN * 8;
+    // barrier indices inside the header
+    static __device__ __forceinline__ constexpr int bar_full(int s, int slot) { return s * kStg + slot; }
+    static __device__ __forceinline__ constexpr int bar_rd(int s, int e) { return 2 * kStg + s * 2 + (e - 1); }
+};
 
 __device__ __forceinline__ void lds16x16(uint32_t base, uint32_t (&raw)[16])
 {
@@ -116,13 +124,18 @@ __device__ __forceinline__ void rd_wait(uint32_t bar, int j) { mbar_wait(bar, (u
 //   scratch[spec][ko][4096]; CTA c is bound to ONE outer bin ko = c % M for its whole life and to the
 //   spectra spec = part, part + P, ... (part = c / M, P = gridDim / M) of the batch, so its private
 //   accumulator row is just 4096 doubles in natural order k (L2 resident, coalesced);
-//   reduce_rows_fourstep() maps (ko, k) -> bin ko + M k.  The complex rows are prefetched with plain
-//   coalesced LDG.64 one stage ahead, into the registers of the idle stream.
+//   reduce_rows_fourstep() maps (ko, k) -> bin ko + M k.  The complex rows travel through the same TMA ring
+//   as the raw bytes (one 32 KiB bulk copy per row), so the loop is the same for both sources; only the
+//   pass-1 input differs (LDS.64 of complex values instead of LDS.U16 + unpack).
 template <bool WINDOW, bool SRC_C32>
 __global__ void __launch_bounds__(kThreads, 1)
 pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx, int64_t nspec, int M,
                 const float2 *__restrict__ twiddle, const float *__restrict__ window, double *__restrict__ rows)
 {
+    using P = Plan<SRC_C32>;
+    constexpr int kStg = P::kStg, kSlot = P::kSlot;
+    auto bar_full = [](int s, int slot) { return P::bar_full(s, slot); };
+    auto bar_rd = [](int s, int e) { return P::bar_rd(s, e); };
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sm = smem_u32(smem);
     const int tid = threadIdx.x;
@@ -172,10 +185,10 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     // shared-memory addresses (stream B = +kSpecBytes in the ring, +32 KiB in S1/S2)
     const uint32_t ring = sm + kHdrP;                            // [stream][slot][8 KiB]
     const uint32_t raw_off = 2 * tid;                            // + n1 * 512
-    const uint32_t s1_st = sm + kS1Off + tid * 128 + ((tid & 7) << 4);
-    const uint32_t s1_ld = sm + kS1Off + hi * 128 + ((((lo >> 1) ^ (hi & 7)) << 4) | ((lo & 1) << 3));   // + n2 * 2048
-    const uint32_t s2_st = sm + kS2Off + hi * 128 + lo * 8;                                              // + k2 * 2048
-    const uint32_t s2_ld = sm + kS2Off + hi * 2048 + lo * 8;                                             // + n3 * 128
+    const uint32_t s1_st = sm + P::kS1 + tid * 128 + ((tid & 7) << 4);
+    const uint32_t s1_ld = sm + P::kS1 + hi * 128 + ((((lo >> 1) ^ (hi & 7)) << 4) | ((lo & 1) << 3));   // + n2 * 2048
+    const uint32_t s2_st = sm + P::kS2 + hi * 128 + lo * 8;                                              // + k2 * 2048
+    const uint32_t s2_ld = sm + P::kS2 + hi * 2048 + lo * 8;                                             // + n3 * 128
     constexpr uint32_t kStreamS = kN * 8;                        // S1/S2 stream stride
 
     double *row = rows + (size_t)blockIdx.x * kN;
@@ -195,43 +208,34 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 #endif
         }
     };
-    // four-step: row of complex64 for (stream s, local iteration j)
-    auto crow = [&](int s, int j) -> const float2 * {
-        const int64_t spec = (int64_t)part + (int64_t)nparts * (2 * j + s);
-        return cplx + ((size_t)spec * M + ko) * (size_t)kN + tid;
-    };
-    auto ldg16 = [&](const float2 *src, c32 (&v)[16]) {
-#pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) v[n1] = __ldg(src + n1 * 256);
-    };
-
-    // ---- TMA: one 8 KiB bulk copy per (stream, iteration) ------------------------------------
+    // ---- TMA: one bulk copy (8 KiB of bytes / 32 KiB complex row) per (stream, iteration) ------
     const uint8_t *cta_bytes = SRC_C32 ? nullptr : bytes + (size_t)p0 * 2 * kSpecBytes;
     // Ring slots are filled for A: iterations 0..nit (one past the end), B: 0..nit-1, so that every stage of
     // every iteration waits and loads unconditionally; slots that have no spectrum of their own (B of an odd
     // tail, A of iteration nit) re-read the last valid spectrum and their result is never accumulated.
     const int last_valid = 2 * nit - 1 - (lastB_missing ? 1 : 0);
-    auto issue = [&](int s, int j) {                 // thread 0 only; spectrum 2 (p0 + j) + s
-        if (SRC_C32) return;
-        const int slot = j % kStagesP;
+    auto issue = [&](int s, int j) {                 // thread 0 only; my spectrum / row number 2 j + s
+        const int slot = j % kStg;
         const uint32_t bar = sm + 8 * bar_full(s, slot);
         const int idx = min(2 * j + s, last_valid);
+        const void *src = SRC_C32 ? (const void *)(cplx + ((size_t)((int64_t)part + (int64_t)nparts * idx) * M + ko) * (size_t)kN)
+                                  : (const void *)(cta_bytes + (size_t)idx * kSpecBytes);
 #if RPF_TMA_FENCE
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
-        mbar_expect_tx(bar, kSpecBytes);
-        tma_load_1d(ring + (s * kStagesP + slot) * kSpecBytes, cta_bytes + (size_t)idx * kSpecBytes, kSpecBytes, bar);
+        mbar_expect_tx(bar, kSlot);
+        tma_load_1d(ring + (s * kStg + slot) * kSlot, src, kSlot, bar);
     };
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 2 * kStagesP; i++) mbar_init(sm + 8 * i, 1);
+        for (int i = 0; i < 2 * kStg; i++) mbar_init(sm + 8 * i, 1);
 #pragma unroll
-        for (int i = 0; i < 4; i++) mbar_init(sm + 8 * (2 * kStagesP + i), kThreads / 32);
+        for (int i = 0; i < 4; i++) mbar_init(sm + 8 * (2 * kStg + i), kThreads / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (tid == 0)
-        for (int j = 0; j < kStagesP; j++) {
+        for (int j = 0; j < kStg; j++) {
             if (j <= nit) issue(0, j);
             if (j < nit) issue(1, j);
         }
@@ -276,17 +280,19 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         }
     };
 
+    // pass-1 input of one spectrum from its ring slot: raw bytes (unpacked at the top of the consuming stage)
+    // or the complex row straight into the idle stream's registers
+    auto load_input = [&](uint32_t slot_addr, c32 (&v)[16]) {
+        if (SRC_C32) lds64x16<2048>(slot_addr + tid * 8, v);
+        else lds16x16(slot_addr + raw_off, raw);
+    };
     // prologue: input of stream A, iteration 0
-    if (SRC_C32) {
-        ldg16(crow(0, 0), vA);
-    } else {
-        mbar_wait(sm + 8 * bar_full(0, 0), 0);
-        lds16x16(ring + raw_off, raw);
-    }
+    mbar_wait(sm + 8 * bar_full(0, 0), 0);
+    load_input(ring, vA);
 
     int since_flush = 0;
     for (int j = 0; j < nit; j++) {
-        const int slot = j % kStagesP;
+        const int slot = j % kStg;
         const uint32_t ph = (uint32_t)(j & 1);
         const bool haveB = !(lastB_missing && j == nit - 1);
 
@@ -309,39 +315,32 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         using PosS2 = std::integral_constant<int, RPF_LOADPOS_S2>;
         const uint32_t rd = sm + 8 * bar_rd(0, 1);       // bar_rd(s, e) = rd + 8 (2 s + e - 1)
         auto fetch_rawB = [&]() {
-            const uint32_t bar = sm + 8 * bar_full(1, slot), par = (uint32_t)((j / kStagesP) & 1);
+            const uint32_t bar = sm + 8 * bar_full(1, slot), par = (uint32_t)((j / kStg) & 1);
             mbar_wait(bar, par);
-            lds16x16(ring + (kStagesP + slot) * kSpecBytes + raw_off, raw);
+            load_input(ring + (kStg + slot) * kSlot, vB);
         };
         auto fetch_s1A = [&]() {
             mbar_wait(rd, ph);                               // every warp has stored its (A,1) rows ...
-            if (issuer(j + kStagesP <= nit)) issue(0, j + kStagesP);         // ... so A's ring slot is free
+            if (issuer(j + kStg <= nit)) issue(0, j + kStg);         // ... so A's ring slot is free
             lds64x16<2048>(s1_ld, vA);
         };
         auto fetch_s1B = [&]() {
             mbar_wait(rd + 16, ph);
-            if (issuer(j + kStagesP < nit)) issue(1, j + kStagesP);
+            if (issuer(j + kStg < nit)) issue(1, j + kStg);
             lds64x16<2048>(s1_ld + kStreamS, vB);
         };
         auto fetch_s2A = [&]() { mbar_wait(rd + 8, ph); lds64x16<128>(s2_ld, vA); };
         auto fetch_s2B = [&]() { mbar_wait(rd + 24, ph); lds64x16<128>(s2_ld + kStreamS, vB); };
         auto fetch_rawA = [&]() {
-            const uint32_t bar = sm + 8 * bar_full(0, (j + 1) % kStagesP), par = (uint32_t)(((j + 1) / kStagesP) & 1);
+            const uint32_t bar = sm + 8 * bar_full(0, (j + 1) % kStg), par = (uint32_t)(((j + 1) / kStg) & 1);
             mbar_wait(bar, par);
-            lds16x16(ring + ((j + 1) % kStagesP) * kSpecBytes + raw_off, raw);
+            load_input(ring + ((j + 1) % kStg) * kSlot, vA);
         };
 
         // ---- (A,1)  | prefetch raw B ---------------------------------------------------------
-        if (SRC_C32) {
-            dft16_first(vA);
-            if (haveB) ldg16(crow(1, j), vB);
-            dft16_second(vA);
-            post1(vA, 0, none);
-        } else {
-            unpack(vA);
-            radix(vA, PosRaw(), fetch_rawB);
-            if (PosRaw::value == 3) post1(vA, 0, fetch_rawB); else post1(vA, 0, none);
-        }
+        if (!SRC_C32) unpack(vA);
+        radix(vA, PosRaw(), fetch_rawB);
+        if (PosRaw::value == 3) post1(vA, 0, fetch_rawB); else post1(vA, 0, none);
 
         // ---- (B,1)  | prefetch S1[A] ----------------------------------------------------------
         if (!SRC_C32) unpack(vB);
@@ -362,14 +361,8 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         power(vA);
 
         // ---- (B,3)  | prefetch raw A of the next iteration ------------------------------------
-        if (SRC_C32) {
-            dft16_first(vB);
-            if (j + 1 < nit) ldg16(crow(0, j + 1), vA);
-            dft16_second(vB);
-        } else {
-            radix(vB, PosRaw(), fetch_rawA);
-            if (PosRaw::value == 3) fetch_rawA();
-        }
+        radix(vB, PosRaw(), fetch_rawA);
+        if (PosRaw::value == 3) fetch_rawA();
         if (haveB) power(vB);
 
         if (++since_flush == kFlushPairs) { flush(); since_flush = 0; }
@@ -381,26 +374,26 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 
 cudaError_t rpf_pipe4096_configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(pipe4096_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemP);
+    cudaError_t e = cudaFuncSetAttribute(pipe4096_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Plan<false>::kSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(pipe4096_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemP);
+    e = cudaFuncSetAttribute(pipe4096_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Plan<false>::kSmem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(pipe4096_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemP);
+    return cudaFuncSetAttribute(pipe4096_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Plan<true>::kSmem);
 }
 
 cudaError_t rpf_launch_pipe4096(const RpfLaunch &L)
 {
     if (L.cplx) {   // four-step inner transform: the grid is fixed (multiple of M) so CTA <-> outer bin is stable
         if (L.nspec <= 0) return cudaSuccess;
-        pipe4096_kernel<false, true><<<L.grid, kThreads, kSmemP, L.stream>>>(nullptr, L.cplx, L.nspec, L.M, L.twiddle, nullptr, L.rows);
+        pipe4096_kernel<false, true><<<L.grid, kThreads, Plan<true>::kSmem, L.stream>>>(nullptr, L.cplx, L.nspec, L.M, L.twiddle, nullptr, L.rows);
         return cudaGetLastError();
     }
     const int64_t npairs = (L.nspec + 1) / 2;
     if (npairs <= 0) return cudaSuccess;
     dim3 grid((unsigned)(npairs < L.grid ? npairs : L.grid)), block(kThreads);
     if (L.window)
-        pipe4096_kernel<true, false><<<grid, block, kSmemP, L.stream>>>(L.bytes, nullptr, L.nspec, 1, L.twiddle, L.window, L.rows);
+        pipe4096_kernel<true, false><<<grid, block, Plan<false>::kSmem, L.stream>>>(L.bytes, nullptr, L.nspec, 1, L.twiddle, L.window, L.rows);
     else
-        pipe4096_kernel<false, false><<<grid, block, kSmemP, L.stream>>>(L.bytes, nullptr, L.nspec, 1, L.twiddle, nullptr, L.rows);
+        pipe4096_kernel<false, false><<<grid, block, Plan<false>::kSmem, L.stream>>>(L.bytes, nullptr, L.nspec, 1, L.twiddle, nullptr, L.rows);
     return cudaGetLastError();
 }
