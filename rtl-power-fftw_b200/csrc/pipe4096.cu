@@ -82,16 +82,11 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar)
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
-// Wait until every warp has arrived for iteration j.  (A polled shared-memory counter was tried in
-// place of the mbarrier: 15 % slower -- spinning warps burn issue slots and LSU bandwidth, whereas
-// try_wait parks the warp in hardware.)
-__device__ __forceinline__ void rd_wait(uint32_t bar, int j) { mbar_wait(bar, (uint32_t)(j & 1)); }
 
 // Stage scheduling knobs (measured on B200):
 //   RPF_LOADPOS  where, inside stage (Y,p), the wait for X's barrier and X's 16 loads sit:
 //                0 after the first half of Y's radix-16, 1 after three quarters, 2 after all of it,
 //                3 after the twiddle multiplications (just before Y's stores)
-//   RPF_PROBE    1: issue one try_wait at the top of the stage and branch on its answer at the wait point
 #ifndef RPF_LOADPOS
 #define RPF_LOADPOS 2
 #endif
@@ -104,19 +99,6 @@ __device__ __forceinline__ void rd_wait(uint32_t bar, int j) { mbar_wait(bar, (u
 #endif
 #ifndef RPF_LOADPOS_S2
 #define RPF_LOADPOS_S2 RPF_LOADPOS
-#endif
-#ifndef RPF_PROBE
-#define RPF_PROBE 0
-#endif
-//   RPF_POWER2   1: |X|^2 accumulated as packed (re^2, im^2) pairs (one FFMA2 per bin instead of two FFMA)
-//   RPF_TMA_FENCE 1: fence.proxy.async before re-filling a ring slot.  Not needed: the slot was only READ
-//                through the generic proxy and those loads have completed (their values were stored to S1
-//                before the barrier that frees the slot), the standard TMA-load pipeline has no fence there.
-#ifndef RPF_TMA_FENCE
-#define RPF_TMA_FENCE 0
-#endif
-#ifndef RPF_POWER2
-#define RPF_POWER2 0
 #endif
 
 // SRC_C32 = false: spectra come as raw bytes (TMA ring), bins are flushed fftshifted.
@@ -172,15 +154,9 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) win[n1] = window[n1 * 256 + tid];
     }
-#if RPF_POWER2
-    c32 acc[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) acc[k] = make_float2(0.0f, 0.0f);
-#else
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) acc[k] = 0.0f;
-#endif
 
     // shared-memory addresses (stream B = +kSpecBytes in the ring, +32 KiB in S1/S2)
     const uint32_t ring = sm + kHdrP;                            // [stream][slot][8 KiB]
@@ -199,13 +175,8 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         for (int k3 = 0; k3 < 16; k3++) cur[k3] = row[(tid + 256 * k3 + kShift) & (kN - 1)];
 #pragma unroll
         for (int k3 = 0; k3 < 16; k3++) {
-#if RPF_POWER2
-            row[(tid + 256 * k3 + kShift) & (kN - 1)] = cur[k3] + ((double)acc[k3].x + (double)acc[k3].y);
-            acc[k3] = make_float2(0.0f, 0.0f);
-#else
             row[(tid + 256 * k3 + kShift) & (kN - 1)] = cur[k3] + (double)acc[k3];   // bin k = tid + 256 k3
             acc[k3] = 0.0f;
-#endif
         }
     };
     // ---- TMA: one bulk copy (8 KiB of bytes / 32 KiB complex row) per (stream, iteration) ------
@@ -220,9 +191,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         const int idx = min(2 * j + s, last_valid);
         const void *src = SRC_C32 ? (const void *)(cplx + ((size_t)((int64_t)part + (int64_t)nparts * idx) * M + ko) * (size_t)kN)
                                   : (const void *)(cta_bytes + (size_t)idx * kSpecBytes);
-#if RPF_TMA_FENCE
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
+        // no proxy fence: the slot was only read through the generic proxy and those loads have completed
         mbar_expect_tx(bar, kSlot);
         tma_load_1d(ring + (s * kStg + slot) * kSlot, src, kSlot, bar);
     };
@@ -271,13 +240,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     };
     auto power = [&](const c32 (&v)[16]) {
 #pragma unroll
-        for (int k3 = 0; k3 < 16; k3++) {
-#if RPF_POWER2
-            acc[k3] = __ffma2_rn(v[k3], v[k3], acc[k3]);
-#else
-            acc[k3] = fmaf(v[k3].x, v[k3].x, fmaf(v[k3].y, v[k3].y, acc[k3]));
-#endif
-        }
+        for (int k3 = 0; k3 < 16; k3++) acc[k3] = fmaf(v[k3].x, v[k3].x, fmaf(v[k3].y, v[k3].y, acc[k3]));
     };
 
     // pass-1 input of one spectrum from its ring slot: raw bytes (unpacked at the top of the consuming stage)

@@ -35,43 +35,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     } while (!done);
 }
 
-// elect.sync: true in exactly one lane of a converged warp
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-
-// One try_wait (may suspend for the hardware time limit, returns whether the phase completed).
-__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity)
-{
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done;
-}
-
-// Non-blocking probe (mbarrier.test_wait): issue it early, consume the answer later, and only fall
-// back to the (suspending, ~90-cycle) try_wait loop when the phase really has not completed yet.
-__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity)
-{
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done;
-}
-
 // u8 pair (I | Q<<8) -> complex float carrying a +32768 offset on both rails:
 // PRMT builds 0x4700XX00 = 32768.0f + XX exactly (byte into mantissa bits 15:8).
 // No window: the offset (32768+127 per rail) is left in; every butterfly sum of
@@ -88,17 +51,3 @@ __device__ __forceinline__ c32 unpack_biased(uint32_t raw)
     return v;
 }
 constexpr float kBias = 32768.0f + 127.0f;
-
-
-// Compiler scheduling fence for 16 complex registers: the values must be materialised here and
-// nothing that uses them afterwards can be hoisted above this point (asm volatile statements keep
-// their relative order, so this pins butterfly code to one side of a bar.sync / bar.arrive).
-__device__ __forceinline__ void pin16(c32 (&v)[16])
-{
-    asm volatile("" : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[2].x), "+f"(v[2].y), "+f"(v[3].x),
-                      "+f"(v[3].y), "+f"(v[4].x), "+f"(v[4].y), "+f"(v[5].x), "+f"(v[5].y), "+f"(v[6].x), "+f"(v[6].y),
-                      "+f"(v[7].x), "+f"(v[7].y) :: "memory");
-    asm volatile("" : "+f"(v[8].x), "+f"(v[8].y), "+f"(v[9].x), "+f"(v[9].y), "+f"(v[10].x), "+f"(v[10].y), "+f"(v[11].x),
-                      "+f"(v[11].y), "+f"(v[12].x), "+f"(v[12].y), "+f"(v[13].x), "+f"(v[13].y), "+f"(v[14].x), "+f"(v[14].y),
-                      "+f"(v[15].x), "+f"(v[15].y) :: "memory");
-}
