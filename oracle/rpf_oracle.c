@@ -13,7 +13,7 @@
  *   (1) oracle/_ref: the reference's *own* src/datastore.cxx compiled from
  *       /root/reference against an fftw3.h shim -- identical loop, carry-over,
  *       truncation, index order and double accumulation; only the DFT routine
- *       is a stand-in (tests/test_oracle_vs_ref.py),
+ *       is a stand-in (tests/test_oracle.py, tests/test_golden.py),
  *   (2) the DFT definition (forward, exp(-2 pi i nk/N), unnormalised,
  *       FFTW_FORWARD at src/datastore.cxx:33) cross-checked against numpy's
  *       float64 pocketfft and an O(N^2) long-double DFT,
