@@ -216,10 +216,9 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) {
             c32 x = unpack_biased(raw[n1]);
-            if (WINDOW) {        // (u8 - 127.0f) * w, one rounding per rail: src/datastore.cxx:75-77
-                x = __fadd2_rn(x, make_float2(-kBias, -kBias));
-                x = __fmul2_rn(x, make_float2(win[n1], win[n1]));
-            }
+            // window: u8 - 127.0f here (exact), the multiplication by w (src/datastore.cxx:76-77) is fused into the
+            // first radix-4 layer of pass 1 (dft16_first_windowed)
+            if (WINDOW) x = __fadd2_rn(x, make_float2(-kBias, -kBias));
             v[n1] = x;
         }
     };
@@ -263,10 +262,10 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         auto none = []() {};
         // thread 0 issues the bulk copies (a warp-uniform branch with elect.sync was measured 14 % slower)
         auto issuer = [&](bool cond) -> bool { return tid == 0 && cond; };
-        auto radix = [&](c32 (&vY)[16], auto pos, auto &&fetch) {
+        auto radix = [&](c32 (&vY)[16], auto pos, auto &&fetch, bool pass1 = false) {
             constexpr int kPos = decltype(pos)::value;
             c32 y[16];
-            dft16_first(vY);
+            if (WINDOW && !SRC_C32 && pass1) dft16_first_windowed(vY, win); else dft16_first(vY);
             if (kPos == 0) fetch();
             dft16_second_a(vY, y);
             if (kPos == 1) fetch();
@@ -302,12 +301,12 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 
         // ---- (A,1)  | prefetch raw B ---------------------------------------------------------
         if (!SRC_C32) unpack(vA);
-        radix(vA, PosRaw(), fetch_rawB);
+        radix(vA, PosRaw(), fetch_rawB, true);
         if (PosRaw::value == 3) post1(vA, 0, fetch_rawB); else post1(vA, 0, none);
 
         // ---- (B,1)  | prefetch S1[A] ----------------------------------------------------------
         if (!SRC_C32) unpack(vB);
-        radix(vB, PosS1(), fetch_s1A);
+        radix(vB, PosS1(), fetch_s1A, true);
         if (PosS1::value == 3) post1(vB, 1, fetch_s1A); else post1(vB, 1, none);
 
         // ---- (A,2)  | prefetch S1[B] ----------------------------------------------------------
