@@ -25,7 +25,16 @@
 namespace {
 
 constexpr int kN = 4096;
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;            // compute threads (8 warps)
+// RPF_TMAWARP = 1: a third warp group is launched only so that one of its lanes can issue the bulk copies; the loop of
+// the compute warps then contains no divergent issue code at all.  The copy lane is a registered participant of the
+// two pass-1 exchange barriers (it arrives for phase j as soon as it has seen phase j-1 complete, a whole iteration
+// before the compute warps), so it can neither miss a phase nor hold anybody up.  Registers: launched at 384 x 168,
+// the copy group drops to 24 and the compute groups take 208 (setmaxnreg).
+#ifndef RPF_TMAWARP
+#define RPF_TMAWARP 1
+#endif
+constexpr int kLaunchThreads = kThreads + (RPF_TMAWARP ? 128 : 0);
 #ifndef RPF_FLUSH_PAIRS
 #define RPF_FLUSH_PAIRS 64
 #endif
@@ -110,7 +119,7 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar)
 //   as the raw bytes (one 32 KiB bulk copy per row), so the loop is the same for both sources; only the
 //   pass-1 input differs (LDS.64 of complex values instead of LDS.U16 + unpack).
 template <bool WINDOW, bool SRC_C32>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kLaunchThreads, 1)
 pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx, int64_t nspec, int M,
                 const float2 *__restrict__ twiddle, const float *__restrict__ window, double *__restrict__ rows)
 {
@@ -142,43 +151,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     }
     if (nit <= 0) return;
 
-    // ---- per-thread constants ----------------------------------------------------------------
-    float2 tw1[15], tw2[15];
-#pragma unroll
-    for (int k = 1; k < 16; k++) {
-        tw1[k - 1] = twiddle[(tid * k) & (kN - 1)];             // W_4096^{t k1}, t = tid
-        tw2[k - 1] = twiddle[(hi * k * 16) & (kN - 1)];         // W_256^{n3 k2}, n3 = hi
-    }
-    float win[WINDOW ? 16 : 1];
-    if (WINDOW) {
-#pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) win[n1] = window[n1 * 256 + tid];
-    }
-    float acc[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) acc[k] = 0.0f;
-
-    // shared-memory addresses (stream B = +kSpecBytes in the ring, +32 KiB in S1/S2)
-    const uint32_t ring = sm + kHdrP;                            // [stream][slot][8 KiB]
-    const uint32_t raw_off = 2 * tid;                            // + n1 * 512
-    const uint32_t s1_st = sm + P::kS1 + tid * 128 + ((tid & 7) << 4);
-    const uint32_t s1_ld = sm + P::kS1 + hi * 128 + ((((lo >> 1) ^ (hi & 7)) << 4) | ((lo & 1) << 3));   // + n2 * 2048
-    const uint32_t s2_st = sm + P::kS2 + hi * 128 + lo * 8;                                              // + k2 * 2048
-    const uint32_t s2_ld = sm + P::kS2 + hi * 2048 + lo * 8;                                             // + n3 * 128
-    constexpr uint32_t kStreamS = kN * 8;                        // S1/S2 stream stride
-
-    double *row = rows + (size_t)blockIdx.x * kN;
-    constexpr int kShift = SRC_C32 ? 0 : kN / 2;     // bytes path: fftshift here; four-step: in the reduce kernel
-    auto flush = [&]() {
-        double cur[16];
-#pragma unroll
-        for (int k3 = 0; k3 < 16; k3++) cur[k3] = row[(tid + 256 * k3 + kShift) & (kN - 1)];
-#pragma unroll
-        for (int k3 = 0; k3 < 16; k3++) {
-            row[(tid + 256 * k3 + kShift) & (kN - 1)] = cur[k3] + (double)acc[k3];   // bin k = tid + 256 k3
-            acc[k3] = 0.0f;
-        }
-    };
+    const uint32_t ring = sm + kHdrP;                            // [stream][slot]
     // ---- TMA: one bulk copy (8 KiB of bytes / 32 KiB complex row) per (stream, iteration) ------
     const uint8_t *cta_bytes = SRC_C32 ? nullptr : bytes + (size_t)p0 * 2 * kSpecBytes;
     // Ring slots are filled for A: iterations 0..nit (one past the end), B: 0..nit-1, so that every stage of
@@ -199,16 +172,75 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 #pragma unroll
         for (int i = 0; i < 2 * kStg; i++) mbar_init(sm + 8 * i, 1);
 #pragma unroll
-        for (int i = 0; i < 4; i++) mbar_init(sm + 8 * (2 * kStg + i), kThreads / 32);
+        for (int i = 0; i < 4; i++) mbar_init(sm + 8 * (2 * kStg + i), kThreads / 32 + ((RPF_TMAWARP && (i & 1) == 0) ? 1 : 0));   // index 2 s + e - 1
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+#if RPF_TMAWARP
+    if (tid >= kThreads) {                             // the copy warp group: one lane works
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (tid == kThreads) {
+            for (int j = 0; j < kStg; j++) {
+                if (j <= nit) issue(0, j);
+                if (j < nit) issue(1, j);
+            }
+            for (int j = 0; j < nit; j++) {
+                const uint32_t ph = (uint32_t)(j & 1);
+                mbar_arrive(sm + 8 * bar_rd(0, 1));
+                mbar_wait(sm + 8 * bar_rd(0, 1), ph);                  // every compute warp has stored its (A,1) rows
+                if (j + kStg <= nit) issue(0, j + kStg);               // ... so A's ring slot is free
+                mbar_arrive(sm + 8 * bar_rd(1, 1));
+                mbar_wait(sm + 8 * bar_rd(1, 1), ph);
+                if (j + kStg < nit) issue(1, j + kStg);
+            }
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+#else
     if (tid == 0)
         for (int j = 0; j < kStg; j++) {
             if (j <= nit) issue(0, j);
             if (j < nit) issue(1, j);
         }
+#endif
 
+    // ---- per-thread constants ----------------------------------------------------------------
+    float2 tw1[15], tw2[15];
+#pragma unroll
+    for (int k = 1; k < 16; k++) {
+        tw1[k - 1] = twiddle[(tid * k) & (kN - 1)];             // W_4096^{t k1}, t = tid
+        tw2[k - 1] = twiddle[(hi * k * 16) & (kN - 1)];         // W_256^{n3 k2}, n3 = hi
+    }
+    float win[WINDOW ? 16 : 1];
+    if (WINDOW) {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) win[n1] = window[n1 * 256 + (tid & (kThreads - 1))];   // (copy-group threads: in range)
+    }
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = 0.0f;
+
+    // shared-memory addresses (stream B = +kSpecBytes in the ring, +32 KiB in S1/S2)
+    const uint32_t raw_off = 2 * tid;                            // + n1 * 512
+    const uint32_t s1_st = sm + P::kS1 + tid * 128 + ((tid & 7) << 4);
+    const uint32_t s1_ld = sm + P::kS1 + hi * 128 + ((((lo >> 1) ^ (hi & 7)) << 4) | ((lo & 1) << 3));   // + n2 * 2048
+    const uint32_t s2_st = sm + P::kS2 + hi * 128 + lo * 8;                                              // + k2 * 2048
+    const uint32_t s2_ld = sm + P::kS2 + hi * 2048 + lo * 8;                                             // + n3 * 128
+    constexpr uint32_t kStreamS = kN * 8;                        // S1/S2 stream stride
+
+    double *row = rows + (size_t)blockIdx.x * kN;
+    constexpr int kShift = SRC_C32 ? 0 : kN / 2;     // bytes path: fftshift here; four-step: in the reduce kernel
+    auto flush = [&]() {
+        double cur[16];
+#pragma unroll
+        for (int k3 = 0; k3 < 16; k3++) cur[k3] = row[(tid + 256 * k3 + kShift) & (kN - 1)];
+#pragma unroll
+        for (int k3 = 0; k3 < 16; k3++) {
+            row[(tid + 256 * k3 + kShift) & (kN - 1)] = cur[k3] + (double)acc[k3];   // bin k = tid + 256 k3
+            acc[k3] = 0.0f;
+        }
+    };
     c32 vA[16], vB[16];
     uint32_t raw[16];
 
@@ -261,7 +293,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         // stage (Y,p): radix-16 on Y; `fetch` = wait for X's barrier + X's 16 loads, placed by RPF_LOADPOS
         auto none = []() {};
         // thread 0 issues the bulk copies (a warp-uniform branch with elect.sync was measured 14 % slower)
-        auto issuer = [&](bool cond) -> bool { return tid == 0 && cond; };
+        auto issuer = [&](bool cond) -> bool { return !RPF_TMAWARP && tid == 0 && cond; };
         auto radix = [&](c32 (&vY)[16], auto pos, auto &&fetch, bool pass1 = false) {
             constexpr int kPos = decltype(pos)::value;
             c32 y[16];
@@ -347,12 +379,12 @@ cudaError_t rpf_launch_pipe4096(const RpfLaunch &L)
 {
     if (L.cplx) {   // four-step inner transform: the grid is fixed (multiple of M) so CTA <-> outer bin is stable
         if (L.nspec <= 0) return cudaSuccess;
-        pipe4096_kernel<false, true><<<L.grid, kThreads, Plan<true>::kSmem, L.stream>>>(nullptr, L.cplx, L.nspec, L.M, L.twiddle, nullptr, L.rows);
+        pipe4096_kernel<false, true><<<L.grid, kLaunchThreads, Plan<true>::kSmem, L.stream>>>(nullptr, L.cplx, L.nspec, L.M, L.twiddle, nullptr, L.rows);
         return cudaGetLastError();
     }
     const int64_t npairs = (L.nspec + 1) / 2;
     if (npairs <= 0) return cudaSuccess;
-    dim3 grid((unsigned)(npairs < L.grid ? npairs : L.grid)), block(kThreads);
+    dim3 grid((unsigned)(npairs < L.grid ? npairs : L.grid)), block(kLaunchThreads);
     if (L.window)
         pipe4096_kernel<true, false><<<grid, block, Plan<false>::kSmem, L.stream>>>(L.bytes, nullptr, L.nspec, 1, L.twiddle, L.window, L.rows);
     else
