@@ -1,19 +1,20 @@
-// pipe4096.cu -- N = 4096, two-stream software pipeline.
+// pipe4096.cu -- N = 4096, two-stream software pipeline (the headline kernel).
 //
-// Same arithmetic and shared-memory layouts as fused4096.cu, different schedule.  The butterflies
-// keep the FP32 pipe ~95 % busy when nothing interferes (tools/dftbench.cu), and the staging +
-// exchange traffic alone would run at > 28 % of the HBM roofline, but a CTA whose warps all move
-// through load -> butterfly -> store -> barrier in lock-step serialises the two.  Here every thread
-// carries TWO spectra (streams A and B, 16 values each) and alternates between them:
+// 16 x 16 x 16 decomposition, 16 values per thread, packed FP32.  The butterflies keep the FP32 pipe ~95 %
+// busy when nothing interferes (tools/dftbench.cu), and the staging + exchange traffic alone would run at
+// > 28 % of the HBM roofline, but a CTA whose warps all move through load -> butterfly -> store -> barrier
+// in lock-step serialises the two.  Here every compute thread carries TWO spectra (streams A and B, 16
+// values each) and alternates between them:
 //
-//     stage(Y,p):  first half of the radix-16 on Y
-//                  wait(mbarrier of X's next pass);  issue X's 16 loads      <- hidden under Y's math
-//                  second half of the radix-16 on Y;  twiddle;  store Y;  arrive(mbarrier of Y's pass)
+//     stage(Y,p):  radix-16 on Y
+//                  wait(mbarrier of X's next pass);  issue X's 16 loads      <- land under Y's tail
+//                  twiddle;  store Y;  arrive(mbarrier of Y's pass)
 //
-// with the stage order (A,1)(B,1)(A,2)(B,2)(A,3)(B,3).  Barriers are split mbarrier arrive/wait
-// pairs with half a butterfly of slack, so no warp ever sits in bar.sync; loads have half a
-// butterfly plus the twiddle/store tail to land.  One CTA = 256 threads per SM, <= 255 registers,
-// both twiddle sets in registers, no spills.
+// with the stage order (A,1)(B,1)(A,2)(B,2)(A,3)(B,3).  Barriers are split mbarrier arrive/wait pairs a
+// whole butterfly apart in program order, so no warp ever sits in bar.sync; every stage of every
+// iteration is unconditional (ring slots without a spectrum of their own re-read the last valid one),
+// so the loop has no data-dependent branches.  One CTA per SM: 256 compute threads (both twiddle sets in
+// registers, no spills) plus a third warp group, one lane of which issues the TMA bulk copies.
 //
 // Replaces reference src/datastore.cxx:68-87 for N = 4096.
 #include <stdint.h>
@@ -39,7 +40,7 @@ constexpr int kLaunchThreads = kThreads + (RPF_TMAWARP ? 128 : 0);
 #define RPF_FLUSH_PAIRS 64
 #endif
 #ifndef RPF_PIPE_STAGES
-#define RPF_PIPE_STAGES 2             // measured: 2 -> 587, 3 -> 578 (modulo-3 slot arithmetic), 4 -> 582 Gsamples/s
+#define RPF_PIPE_STAGES 2             // measured (round-1 start): 2 -> 587, 3 -> 578 (modulo-3 slot arithmetic), 4 -> 582 Gsamples/s
 #endif
 constexpr int kStagesP = RPF_PIPE_STAGES;         // TMA ring depth per stream
 constexpr int kSpecBytes = 2 * kN;                // 8 KiB
@@ -292,7 +293,8 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 
         // stage (Y,p): radix-16 on Y; `fetch` = wait for X's barrier + X's 16 loads, placed by RPF_LOADPOS
         auto none = []() {};
-        // thread 0 issues the bulk copies (a warp-uniform branch with elect.sync was measured 14 % slower)
+        // RPF_TMAWARP = 0 only: thread 0 issues the bulk copies inside the loop (a warp-uniform branch with elect.sync
+        // was measured 14 % slower)
         auto issuer = [&](bool cond) -> bool { return !RPF_TMAWARP && tid == 0 && cond; };
         auto radix = [&](c32 (&vY)[16], auto pos, auto &&fetch, bool pass1 = false) {
             constexpr int kPos = decltype(pos)::value;
