@@ -159,7 +159,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     // every iteration waits and loads unconditionally; slots that have no spectrum of their own (B of an odd
     // tail, A of iteration nit) re-read the last valid spectrum and their result is never accumulated.
     const int last_valid = 2 * nit - 1 - (lastB_missing ? 1 : 0);
-    auto issue = [&](int s, int j) {                 // thread 0 only; my spectrum / row number 2 j + s
+    auto issue = [&](int s, int j) {                 // one lane only (the copy lane); my spectrum / row number 2 j + s
         const int slot = j % kStg;
         const uint32_t bar = sm + 8 * bar_full(s, slot);
         const int idx = min(2 * j + s, last_valid);
