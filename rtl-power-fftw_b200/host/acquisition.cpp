@@ -7,6 +7,10 @@
 #include <iostream>
 #include <thread>
 
+// Text grammar of src/acquisition.cxx:32-58, including its corner case: the value kept for a line is whatever the
+// extraction loop leaves in `value` once it stops -- and a FAILED extraction stores 0 (C++11 num_get), so a line such
+// as "0.5 abc" yields 0, not 0.5, while "1 2 3" yields 3.  (Pinned against the reference's own function compiled from
+// /root/reference: tests/test_aux_parser.py.)
 template <typename T> std::vector<T> read_inputfile(std::istream &stream)
 {
     std::vector<T> values;
@@ -14,10 +18,10 @@ template <typename T> std::vector<T> read_inputfile(std::istream &stream)
     while (std::getline(stream, line)) {
         std::istringstream ls(line);
         if ((ls >> std::ws).peek() == '#') continue;          // comment line
-        T value, last = T();
-        bool any = false;
-        while (ls >> value) { last = value; any = true; }     // keep the last number of the line
-        if (any) values.push_back(last);
+        T value = T();
+        unsigned parsed = 0;
+        while (ls >> value) parsed++;                         // the failing extraction that ends the loop zeroes `value`
+        if (parsed > 0) values.push_back(value);              // lines without a number are skipped
     }
     return values;
 }

@@ -130,6 +130,45 @@ def test_auxdata_text_reader(tmp_path):
     assert r.returncode == 5 and "Could not open" in r.stderr
 
 
+def test_auxdata_reader_matches_reference_parser(tmp_path):
+    """AuxData's text grammar against what the reference's OWN read_inputfile<T>() returns
+    (tests/golden/aux_parser.json, generated by tests/golden/make_aux_golden.py from the function
+    compiled out of /root/reference): multi-column lines, comments, and the corner case that a
+    failed extraction zeroes the kept value ("0.5 abc" -> 0, src/acquisition.cxx:48-56)."""
+    import json
+    exe = os.path.join(ROOT, "rtl-power-fftw_b200", "host", "rpf_power_synth")
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "aux_parser.json")))
+    assert cases["trailing_garbage_zeroes"]["double"][:2] == ["0", "0"]
+    checked = 0
+    for name, c in sorted(cases.items()):
+        for opt, key, dtype in (("-w", "float", np.float32), ("-B", "double", np.float64)):
+            text, want = c["text"], list(c[key])       # float and double may keep different lines (1e40 overflows float)
+            if not want:
+                continue
+            if len(want) % 2:                           # the CLI forces N even (src/params.cxx:152-155)
+                text += "\n1\n"
+                want.append("1")
+            n = len(want)
+            f = tmp_path / (name + key + ".txt")
+            f.write_bytes(text.encode())
+            r = subprocess.run([exe, str(n), "1", "0", "1", "1", "0", "5", "0", "0", opt, str(f), "--dump-aux"],
+                               capture_output=True, text=True)
+            assert r.returncode == 0, (name, key, r.stderr)
+            lines = r.stdout.split()
+            at = lines.index("window" if opt == "-w" else "baseline")
+            assert int(lines[at + 1]) == n, (name, key)
+            got = np.array(lines[at + 2:at + 2 + n], dtype=np.float64).astype(dtype)
+            assert np.array_equal(got, np.array(want, dtype=np.float64).astype(dtype)), (name, key)
+            checked += 1
+    assert checked >= 12
+    # where the reference is present (the build container), also compare live
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_read_inputfile")
+    if os.path.exists(ref):
+        for name, c in cases.items():
+            r = subprocess.run([ref, "double"], input=c["text"], capture_output=True, text=True)
+            assert r.stdout.split() == c["double"], name
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with
     the contract's keys; it times the reference's own worker loop (oracle/_ref) on the host cores."""

@@ -265,6 +265,65 @@ def test_linearity_large_config2_shape():
     assert perbin(p50, po) < TOL
 
 
+@pytest.mark.parametrize("N,P,copies", [(65536, 64, 33), (8192, 128, 40), (16384, 64, 40)])
+def test_fourstep_multibatch_single_launch(N, P, copies):
+    """The four-step path loops over scratch-sized batches inside ONE rpf_push_device (csrc/rpf_capi.cu,
+    launch_spectra: 512 spectra per batch at 65536 bins, 4096 at 8192): 2112 / 5120 / 2560 spectra in one call
+    cross 4 / 1 / 1 batch boundaries.  The stream is `copies` repetitions of a P-spectra block, so
+    pwr(copies * P spectra) == copies * pwr(P spectra); the P-block itself is pinned to the float64 oracle.
+    The equality is not bit-exact here (unlike the repeated-push test below): one big launch partitions the
+    spectra differently over the CTAs, so the fp32 first-level sums differ at the 1e-7 level."""
+    import torch
+    block = pkg.synth_fill_host(2 * N * P, 0, seed=0x5EED + 4, mode=1)
+    dev = torch.from_numpy(block).cuda().repeat(copies)
+    torch.cuda.synchronize()
+    with Context(N) as c:
+        c.reset(P)
+        c.push_device(dev.data_ptr(), 2 * N * P)
+        p1, d1 = c.finish()
+        c.reset(P * copies)
+        l0 = c.kernel_launches
+        c.push_device(dev.data_ptr(), dev.numel())
+        batches = (c.kernel_launches - l0) // 2
+        pc, dc = c.finish()
+    assert d1 == P and dc == P * copies
+    assert batches == -(-P * copies // ((256 << 20) // (8 * N)))        # really went through the batch loop
+    assert batches >= 2
+    assert np.max(np.abs(pc - copies * p1) / (copies * p1)) < 2e-6
+    po, _ = ol.oracle_run_stream(N, P, block, buf_length=block.size)
+    assert perbin(p1, po) < TOL and perbin(pc / copies, po) < TOL
+    assert np.argmax(pc) == np.argmax(po)
+
+
+def test_window_linearity_config3_shape():
+    """Config 3 shape (4096 bins, Hann window, 1e7 spectra): a 10,000-spectra device-resident block pushed
+    1,000 times; float64 second level => exactly 1000 x the single-block result (to 1e-9), and the block's
+    first 50 spectra are pinned to the oracle with the same window."""
+    import torch
+    N, P, reps = 4096, 10000, 1000
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32)
+    nbytes = 2 * N * P
+    dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    pkg.synth_fill_device(dev.data_ptr(), nbytes, 0, seed=0x5EED + 3, mode=1)
+    torch.cuda.synchronize()
+    with Context(N, window=w) as c:
+        c.reset(P)
+        c.push_device(dev.data_ptr(), nbytes)
+        p1, d1 = c.finish()
+        c.reset(P * reps)
+        for _ in range(reps):
+            c.push_device(dev.data_ptr(), nbytes)
+        pr, dr = c.finish()
+        c.reset(50)
+        c.push_device(dev.data_ptr(), nbytes)            # truncated at 50 spectra by the repeats limit
+        p50, d50 = c.finish()
+    assert d1 == P and dr == P * reps and d50 == 50
+    assert np.max(np.abs(pr - reps * p1) / (reps * p1)) < 1e-9
+    host = pkg.synth_fill_host(2 * N * 50, 0, seed=0x5EED + 3, mode=1)
+    po, _ = ol.oracle_run_stream(N, 50, host, window=w, buf_length=host.size)
+    assert relmax(p50, po) < TOL and np.max(np.abs(p50 - po) / po) < 1e-4
+
+
 def test_write_data_matches_oracle():
     import ctypes as C
     N, R = 4096, 9
