@@ -9,6 +9,19 @@
  * every function returns RPF_OK (0) or a negative rpf_status and leaves a
  * message retrievable with rpf_strerror().
  *
+ * Several GPUs (what must be sharded is the ONE Datastore / ONE pwr[] of
+ * src/rtl_power_fftw.cxx:112 and the sum of src/datastore.cxx:83-85, read after join at
+ * src/acquisition.cxx:347-357).  Two ways, both ending in exactly one NCCL allreduce(sum) of pwr[N]
+ * (float64) on the compute streams inside rpf_finish / rpf_finish_device / rpf_write_data:
+ *   - one process: rpf_config.devices[] -- rpf_push deals whole spectra over the GPUs (the partial
+ *     spectrum carried between buffers is resolved once, before dealing), ncclCommInitAll;
+ *   - one process per GPU: rpf_comm_unique_id on rank 0, ship the id by any means, then
+ *     rpf_comm_init_rank on every rank's single-GPU context.
+ * repeats_done is the local count of spectra (summed over the context's own GPUs).  Precision: bins are
+ * summed in fp32 over at most 128 spectra per CTA, then in float64 (private rows, fixed-order reduction);
+ * the reference adds every spectrum in double (src/datastore.cxx:84) -- the difference is < 1e-6 relative.
+ * libnccl.so.2 is looked up at run time, and only when a second GPU or rank is involved.
+ *
  * Threading: a context is thread-compatible, not thread-safe -- one caller at
  * a time, possibly a different thread per acquisition (the reference starts a
  * fresh worker thread per hop, src/acquisition.cxx:256).  Every entry point
@@ -29,7 +42,8 @@
 extern "C" {
 #endif
 
-#define RPF_B200_ABI_VERSION 1
+#define RPF_B200_ABI_VERSION 2
+#define RPF_MAX_DEVICES 16
 
 typedef enum rpf_status {
     RPF_OK = 0,
@@ -52,10 +66,22 @@ typedef struct rpf_config {
                                    applied as in src/datastore.cxx:76-77                     */
     int64_t      buf_length;    /* Params::buf_length: typical bytes per push (sizing hint)  */
     uint32_t     flags;         /* RPF_FLAG_*                                                */
-    int32_t      reserved[5];
+    int32_t      n_devices;     /* 0: one GPU, `device`.  > 0: the context spans devices[0..n_devices):
+                                   one Datastore, one pwr[], its spectra dealt over these GPUs and
+                                   summed by one NCCL allreduce in rpf_finish (see below)       */
+    int32_t      devices[RPF_MAX_DEVICES];
+    int32_t      reserved[4];
 } rpf_config;
 
 #define RPF_FLAG_NONE 0u
+/* Experimental (N = 4096, no window): first radix-16 pass on the tensor cores (tcgen05.mma on the exact
+ * 8-bit samples, DFT-16 matrix split hi + lo in fp16, fp32 accumulation in TMEM).  Same results within the
+ * 1e-5 tolerance; not the default.  Ignored for other N / with a window. */
+#define RPF_FLAG_TC_PASS1 1u
+/* rpf_push returns as soon as the host->device copies are ENQUEUED; the caller keeps `bytes` untouched
+ * until the next rpf_push / rpf_sync / rpf_finish on this context returns (so two buffers are in flight
+ * and the PCIe link never idles between buffers).  Without the flag `bytes` is free on return. */
+#define RPF_FLAG_PIPELINED_PUSH 2u
 
 /* Plays the role of fftwf_alloc_complex x2 + fftwf_plan_dft_1d(N, in, out,
  * FFTW_FORWARD, FFTW_MEASURE) in Datastore::Datastore (src/datastore.cxx:30-33):
@@ -111,7 +137,7 @@ int64_t rpf_repeats_done(const rpf_ctx *ctx);
  * (the reference's local fft_pointer, src/datastore.cxx:52). */
 int64_t rpf_fft_pointer(const rpf_ctx *ctx);
 
-/* Run the context on a caller-owned CUDA stream (a cudaStream_t passed as
+/* (single-GPU contexts only) Run the context on a caller-owned CUDA stream (a cudaStream_t passed as
  * void*).  NULL restores the context's own non-blocking stream -- to run on the
  * legacy default stream pass cudaStreamLegacy, not 0.  Synchronises first. */
 int rpf_set_stream(rpf_ctx *ctx, void *cuda_stream);
@@ -119,6 +145,16 @@ int rpf_set_stream(rpf_ctx *ctx, void *cuda_stream);
 /* Message for the last error on this context (or for create failures when
  * ctx is NULL).  Never NULL. */
 const char *rpf_strerror(const rpf_ctx *ctx);
+
+/* ---- one process per GPU: join single-GPU contexts into one integration ----
+ * rpf_comm_unique_id fills `id_out` (id_bytes >= 128) with an ncclUniqueId; every rank passes the same id
+ * to rpf_comm_init_rank (collective: all `nranks` ranks must call it).  Afterwards rpf_finish*,
+ * rpf_write_data and rpf_write_row_f32 return the sum over all ranks and must be called by every rank. */
+int rpf_comm_unique_id(void *id_out, size_t id_bytes);
+int rpf_comm_init_rank(rpf_ctx *ctx, const void *id, size_t id_bytes, int32_t rank, int32_t nranks);
+
+/* Number of GPUs the context spans. */
+int32_t rpf_device_count(const rpf_ctx *ctx);
 
 /* Number of this library's kernel launches issued by the context so far. */
 int64_t rpf_kernel_launches(const rpf_ctx *ctx);
@@ -134,6 +170,11 @@ const char *rpf_plan_name(const rpf_ctx *ctx);
  * baseline: NULL or N host doubles. */
 int rpf_write_data(rpf_ctx *ctx, double tuned_freq, int32_t actual_samplerate, int32_t linear,
                    const double *baseline, double *freq_out, double *val_out);
+
+/* The matrix-mode row of Acquisition::write_data() (src/acquisition.cxx:385-388,400-405): the same values,
+ * narrowed to float, N of them, ready to be appended to the .bin file.  row_out: host, N floats. */
+int rpf_write_row_f32(rpf_ctx *ctx, int32_t actual_samplerate, int32_t linear, const double *baseline,
+                      float *row_out);
 
 /* ---- synthetic IQ source (stands in for Rtlsdr::read, src/device.cxx:92-97) --
  * Counter-based generator, bit-identical on host and device (integer

@@ -304,3 +304,40 @@ void rpf_oracle_write_data(int N, double *pwr, int64_t repeats_done, double tune
         val_out[i] = v - (baseline ? baseline[i] : 0);
     }
 }
+
+/* Plan::Plan, repeats from the integration time at the true sample rate,
+ * src/acquisition.cxx:162-163 (params.repeats is int64_t, the product is
+ * evaluated in double). */
+int64_t rpf_oracle_plan_repeats(int N, int actual_samplerate, double integration_time)
+{
+    return (int64_t)ceil(actual_samplerate * integration_time / N);
+}
+
+/* Plan::Plan, list of centre frequencies, src/acquisition.cxx:180-198.
+ * Returns the number of hops; writes at most max_out frequencies.
+ * Types as in the reference: startfreq/stopfreq int64_t (src/params.h:36-37),
+ * min_overlap double (percent), hops and overhang int, list of int64_t
+ * (src/acquisition.h:53) -- so startfreq + samplerate/2.0 is truncated. */
+int rpf_oracle_plan_freqs(int64_t startfreq, int64_t stopfreq, int actual_samplerate, double min_overlap,
+                          int64_t *freqs, int max_out)
+{
+    double min_overhang = actual_samplerate * min_overlap / 100;                                    /* :181 */
+    int hops = (int)ceil(((double)(stopfreq - startfreq) - min_overhang) /
+                         ((double)actual_samplerate - min_overhang));                               /* :182 */
+    int n = 0;
+    if (hops > 1) {                                                                                 /* :183 */
+        int overhang = (int)(((int64_t)hops * actual_samplerate - (stopfreq - startfreq)) / (hops - 1));   /* :184 */
+        int64_t f = (int64_t)(startfreq + actual_samplerate / 2.0);                                 /* :185 */
+        if (n < max_out) freqs[n] = f;
+        n++;
+        for (int hop = 1; hop < hops; hop++) {                                                      /* :187-189 */
+            f = f + actual_samplerate - overhang;
+            if (n < max_out) freqs[n] = f;
+            n++;
+        }
+    } else {
+        if (n < max_out) freqs[n] = (startfreq + stopfreq) / 2;                                     /* :192 */
+        n++;
+    }
+    return n;
+}

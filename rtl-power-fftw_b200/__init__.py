@@ -8,5 +8,6 @@ identifier: ``importlib.import_module("rtl-power-fftw_b200")``.
 
 There is no CPU fallback: if the library is missing, importing ``capi`` raises.
 """
+from . import capi  # noqa: F401
 from .capi import (RpfError, Context, lib, synth_fill_host, synth_fill_device, LIB_PATH,  # noqa: F401
-                   EXPORTED_SYMBOLS)
+                   EXPORTED_SYMBOLS, comm_unique_id)

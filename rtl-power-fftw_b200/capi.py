@@ -5,13 +5,17 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("RPF_B200_LIB", os.path.join(HERE, "librpf_b200.so"))   # override: dev A/B only
+LIB_PATH = os.path.join(HERE, "librpf_b200.so")
+RPF_FLAG_TC_PASS1 = 1
+RPF_FLAG_PIPELINED_PUSH = 2
+RPF_MAX_DEVICES = 16
 
 EXPORTED_SYMBOLS = [
     "rpf_abi_version", "rpf_create", "rpf_destroy", "rpf_reset", "rpf_push", "rpf_push_device", "rpf_sync",
     "rpf_finish", "rpf_finish_device", "rpf_repeats_done", "rpf_fft_pointer", "rpf_set_stream", "rpf_strerror",
     "rpf_kernel_launches", "rpf_plan_name", "rpf_write_data", "rpf_synth_fill_host", "rpf_synth_fill_device",
     "rpf_host_alloc", "rpf_host_free", "rpf_host_register", "rpf_host_unregister",
+    "rpf_comm_unique_id", "rpf_comm_init_rank", "rpf_device_count", "rpf_write_row_f32",
 ]
 
 RPF_OK, RPF_ERR_INVALID_ARG, RPF_ERR_UNSUPPORTED_N, RPF_ERR_CUDA, RPF_ERR_NOMEM, RPF_ERR_STATE = 0, -1, -2, -3, -4, -5
@@ -19,7 +23,8 @@ RPF_OK, RPF_ERR_INVALID_ARG, RPF_ERR_UNSUPPORTED_N, RPF_ERR_CUDA, RPF_ERR_NOMEM,
 
 class RpfConfig(C.Structure):
     _fields_ = [("N", C.c_int32), ("device", C.c_int32), ("window", C.POINTER(C.c_float)),
-                ("buf_length", C.c_int64), ("flags", C.c_uint32), ("reserved", C.c_int32 * 5)]
+                ("buf_length", C.c_int64), ("flags", C.c_uint32), ("n_devices", C.c_int32),
+                ("devices", C.c_int32 * RPF_MAX_DEVICES), ("reserved", C.c_int32 * 4)]
 
 
 class RpfError(RuntimeError):
@@ -71,9 +76,15 @@ def lib():
     L.rpf_host_free.restype = None
     L.rpf_host_register.argtypes = [vp, C.c_size_t]
     L.rpf_host_unregister.argtypes = [vp]
+    L.rpf_comm_unique_id.argtypes = [vp, C.c_size_t]
+    L.rpf_comm_init_rank.argtypes = [vp, vp, C.c_size_t, C.c_int32, C.c_int32]
+    L.rpf_device_count.argtypes = [vp]
+    L.rpf_device_count.restype = C.c_int32
+    L.rpf_write_row_f32.argtypes = [vp, C.c_int32, C.c_int32, f64p, vp]
     for name in ("rpf_create", "rpf_reset", "rpf_push", "rpf_push_device", "rpf_sync", "rpf_finish",
                  "rpf_finish_device", "rpf_set_stream", "rpf_write_data", "rpf_synth_fill_device",
-                 "rpf_host_alloc", "rpf_host_register", "rpf_host_unregister"):
+                 "rpf_host_alloc", "rpf_host_register", "rpf_host_unregister", "rpf_comm_unique_id",
+                 "rpf_comm_init_rank", "rpf_write_row_f32"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -91,14 +102,26 @@ def synth_fill_device(ptr, nbytes, stream_offset=0, seed=0x5EED, mode=0, device=
         raise RpfError(rc, "rpf_synth_fill_device")
 
 
+def comm_unique_id():
+    buf = (C.c_char * 128)()
+    rc = lib().rpf_comm_unique_id(buf, 128)
+    if rc:
+        raise RpfError(rc, lib().rpf_strerror(None).decode())
+    return bytes(buf)
+
+
 class Context:
     """Thin RAII wrapper of rpf_ctx.  Method names follow the C ABI."""
 
-    def __init__(self, N, window=None, device=0, buf_length=0):
+    def __init__(self, N, window=None, device=0, buf_length=0, flags=0, devices=None):
         self.N = N
         self._h = C.c_void_p()
         cfg = RpfConfig()
-        cfg.N, cfg.device, cfg.buf_length = N, device, buf_length
+        cfg.N, cfg.device, cfg.buf_length, cfg.flags = N, device, buf_length, flags
+        if devices is not None:
+            cfg.n_devices = len(devices)
+            for i, d in enumerate(devices):
+                cfg.devices[i] = d
         self._w = None
         if window is not None:
             self._w = np.ascontiguousarray(window, dtype=np.float32)
@@ -148,6 +171,22 @@ class Context:
         self._chk(lib().rpf_write_data(self._h, tuned_freq, samplerate, int(linear),
                                        None if b is None else b.ctypes.data, f.ctypes.data, v.ctypes.data))
         return f, v
+
+    def write_row_f32(self, samplerate, linear=False, baseline=None):
+        row = np.empty(self.N, dtype=np.float32)
+        b = None if baseline is None else np.ascontiguousarray(baseline, dtype=np.float64)
+        self._chk(lib().rpf_write_row_f32(self._h, samplerate, int(linear), None if b is None else b.ctypes.data,
+                                          row.ctypes.data))
+        return row
+
+    def comm_init_rank(self, unique_id, rank, nranks):
+        """unique_id: 128 bytes from comm_unique_id() on rank 0 (shipped by the caller)."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._chk(lib().rpf_comm_init_rank(self._h, buf, 128, rank, nranks))
+
+    @property
+    def device_count(self):
+        return lib().rpf_device_count(self._h)
 
     def set_stream(self, cuda_stream):
         self._chk(lib().rpf_set_stream(self._h, cuda_stream))

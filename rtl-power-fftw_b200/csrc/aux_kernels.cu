@@ -117,29 +117,61 @@ fourstep_outer_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const fl
     }
 }
 
-__global__ void reduce_rows_kernel(const double *__restrict__ rows, int nrows, int64_t rowlen, double *__restrict__ pwr)
+// Private float64 rows -> pwr[], parallel over rows AND deterministic: a block covers 32 output bins; its 8 warps
+// each sum the rows r = w, w + 8, ... (in that order, 4 loads in flight), and the 8 partial sums are then added in
+// warp order.  The grouping depends only on `nrows`, so a given sequence of pushes always gives the same bits.
+constexpr int kRedCols = 32, kRedLanes = 8;
+
+__global__ void __launch_bounds__(kRedCols * kRedLanes)
+reduce_rows_kernel(const double *__restrict__ rows, int nrows, int64_t rowlen, double *__restrict__ pwr)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rowlen) return;
+    __shared__ double part[kRedLanes][kRedCols];
+    const int col = threadIdx.x & (kRedCols - 1), lane = threadIdx.x / kRedCols;
+    const int64_t i = (int64_t)blockIdx.x * kRedCols + col;
     double s = 0.0;
-    for (int r = 0; r < nrows; r++) s += rows[(size_t)r * rowlen + i];
-    pwr[i] = s;
+    if (i < rowlen) {
+        int r = lane;
+        for (; r + 3 * kRedLanes < nrows; r += 4 * kRedLanes) {
+            const double a0 = rows[(size_t)r * rowlen + i], a1 = rows[(size_t)(r + kRedLanes) * rowlen + i];
+            const double a2 = rows[(size_t)(r + 2 * kRedLanes) * rowlen + i], a3 = rows[(size_t)(r + 3 * kRedLanes) * rowlen + i];
+            s += a0; s += a1; s += a2; s += a3;
+        }
+        for (; r < nrows; r += kRedLanes) s += rows[(size_t)r * rowlen + i];
+    }
+    part[lane][col] = s;
+    __syncthreads();
+    if (lane == 0 && i < rowlen) {
+        double t = part[0][col];
+#pragma unroll
+        for (int l = 1; l < kRedLanes; l++) t += part[l][col];
+        pwr[i] = t;
+    }
 }
 
 // Four-step: rows[c][k] holds sum |X|^2 of FFT index k of the inner transform for outer bin ko = c % M.
-// pwr[i] (reference order, DC at N/2) = sum over the CTAs bound to that ko, fixed order.
-__global__ void reduce_rows_fourstep_kernel(const double *__restrict__ rows, int nrows, int M, int inner,
-                                            double *__restrict__ pwr)
+// pwr[i] (reference order, DC at N/2) = sum over the CTAs bound to that ko; same fixed-order scheme as above.
+__global__ void __launch_bounds__(kRedCols * kRedLanes)
+reduce_rows_fourstep_kernel(const double *__restrict__ rows, int nrows, int M, int inner, double *__restrict__ pwr)
 {
+    __shared__ double part[kRedLanes][kRedCols];
+    const int col = threadIdx.x & (kRedCols - 1), lane = threadIdx.x / kRedCols;
     const int64_t n = (int64_t)M * inner;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int64_t bin = (i + n / 2) & (n - 1);          // undo the fftshift: i = (bin + n/2) mod n
-    const int ko = (int)(bin % M);
-    const int64_t k = bin / M;
+    const int64_t i = (int64_t)blockIdx.x * kRedCols + col;
     double s = 0.0;
-    for (int c = ko; c < nrows; c += M) s += rows[(size_t)c * inner + k];
-    pwr[i] = s;
+    if (i < n) {
+        const int64_t bin = (i + n / 2) & (n - 1);          // undo the fftshift: i = (bin + n/2) mod n
+        const int ko = (int)(bin % M);
+        const int64_t k = bin / M;
+        for (int c = ko + lane * M; c < nrows; c += kRedLanes * M) s += rows[(size_t)c * inner + k];
+    }
+    part[lane][col] = s;
+    __syncthreads();
+    if (lane == 0 && i < n) {
+        double t = part[0][col];
+#pragma unroll
+        for (int l = 1; l < kRedLanes; l++) t += part[l][col];
+        pwr[i] = t;
+    }
 }
 
 __global__ void synth_kernel(uint8_t *bytes, size_t len, uint64_t off, uint64_t seed, int mode)
@@ -161,19 +193,23 @@ __global__ void synth_kernel(uint8_t *bytes, size_t len, uint64_t off, uint64_t 
     }
 }
 
-// Acquisition::write_data, reference src/acquisition.cxx:377,390-399.
+// Acquisition::write_data, reference src/acquisition.cxx:377,390-399 (+ the float32 matrix row of :400-405).
 __global__ void write_data_kernel(const double *__restrict__ pwr, int N, int64_t repeats_done, double tuned_freq,
                                   int samplerate, int linear, const double *__restrict__ baseline,
-                                  double *__restrict__ freq_out, double *__restrict__ val_out)
+                                  double *__restrict__ freq_out, double *__restrict__ val_out, float *__restrict__ row_out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     double p = pwr[i];
-    if (i == N / 2) p = (pwr[N / 2 - 1] + pwr[N / 2 + 1]) / 2;            // :377
+    // :377 reads pwr[N/2 + 1]: for N = 2 that is one past the end of the vector in the reference (undefined there);
+    // here the index wraps, i.e. the DC bin becomes the mean of its only two neighbours pwr[0], pwr[0].
+    if (i == N / 2) p = (pwr[N / 2 - 1] + pwr[(N / 2 + 1) % N]) / 2;
     if (freq_out) freq_out[i] = tuned_freq + (i - N / 2.0) * samplerate / N;   // :391
     double v = p / repeats_done / N / samplerate;                          // :393,397
     if (!linear) v = 10 * log10(v);
-    val_out[i] = v - (baseline ? baseline[i] : 0);
+    v -= (baseline ? baseline[i] : 0);
+    val_out[i] = v;
+    if (row_out) row_out[i] = (float)v;                                    // :404 fpwrdb = pwrdb
 }
 
 }  // namespace
@@ -188,10 +224,10 @@ cudaError_t rpf_launch_small(int N, const RpfLaunch &L)
 
 template <int M>
 static cudaError_t launch_outer(const uint8_t *bytes, int64_t nspec, const float2 *twbig, const float *window,
-                                float2 *scratch, cudaStream_t stream)
+                                float2 *scratch, int sms, cudaStream_t stream)
 {
     // whole 4096-thread rows: 16 blocks of 256 per row, about 16 rows' worth of blocks per wave
-    int64_t rows = nspec < 148 ? nspec : 148;
+    int64_t rows = nspec < sms ? nspec : sms;
     const int blocks = (int)(rows * 16);
     if (window)
         fourstep_outer_kernel<M, true><<<blocks, 256, 0, stream>>>(bytes, nspec, twbig, window, scratch);
@@ -201,46 +237,46 @@ static cudaError_t launch_outer(const uint8_t *bytes, int64_t nspec, const float
 }
 
 cudaError_t rpf_launch_fourstep_outer(int M, const uint8_t *bytes, int64_t nspec, const float2 *twbig,
-                                      const float *window, float2 *scratch, cudaStream_t stream)
+                                      const float *window, float2 *scratch, int sms, cudaStream_t stream)
 {
     if (nspec <= 0) return cudaSuccess;
     switch (M) {
-        case 2: return launch_outer<2>(bytes, nspec, twbig, window, scratch, stream);
-        case 4: return launch_outer<4>(bytes, nspec, twbig, window, scratch, stream);
-        case 8: return launch_outer<8>(bytes, nspec, twbig, window, scratch, stream);
-        case 16: return launch_outer<16>(bytes, nspec, twbig, window, scratch, stream);
+        case 2: return launch_outer<2>(bytes, nspec, twbig, window, scratch, sms, stream);
+        case 4: return launch_outer<4>(bytes, nspec, twbig, window, scratch, sms, stream);
+        case 8: return launch_outer<8>(bytes, nspec, twbig, window, scratch, sms, stream);
+        case 16: return launch_outer<16>(bytes, nspec, twbig, window, scratch, sms, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
 cudaError_t rpf_launch_reduce_rows(const double *rows, int nrows, int64_t rowlen, double *pwr, cudaStream_t stream)
 {
-    reduce_rows_kernel<<<(unsigned)((rowlen + 255) / 256), 256, 0, stream>>>(rows, nrows, rowlen, pwr);
+    reduce_rows_kernel<<<(unsigned)((rowlen + kRedCols - 1) / kRedCols), kRedCols * kRedLanes, 0, stream>>>(rows, nrows, rowlen, pwr);
     return cudaGetLastError();
 }
 
 cudaError_t rpf_launch_reduce_rows_fourstep(const double *rows, int nrows, int M, int inner, double *pwr, cudaStream_t stream)
 {
     const int64_t n = (int64_t)M * inner;
-    reduce_rows_fourstep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rows, nrows, M, inner, pwr);
+    reduce_rows_fourstep_kernel<<<(unsigned)((n + kRedCols - 1) / kRedCols), kRedCols * kRedLanes, 0, stream>>>(rows, nrows, M, inner, pwr);
     return cudaGetLastError();
 }
 
-cudaError_t rpf_launch_synth(uint8_t *bytes, size_t len, uint64_t off, uint64_t seed, int mode, cudaStream_t stream)
+cudaError_t rpf_launch_synth(uint8_t *bytes, size_t len, uint64_t off, uint64_t seed, int mode, int sms, cudaStream_t stream)
 {
     if (len == 0) return cudaSuccess;
     const uint64_t words = (len + 15) / 8;
     int blocks = (int)((words + 255) / 256);
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks > sms * 32) blocks = sms * 32;
     synth_kernel<<<blocks, 256, 0, stream>>>(bytes, len, off, seed, mode);
     return cudaGetLastError();
 }
 
 cudaError_t rpf_launch_write_data(const double *pwr, int N, int64_t repeats_done, double tuned_freq, int samplerate,
                                   int linear, const double *baseline, double *freq_out, double *val_out,
-                                  cudaStream_t stream)
+                                  float *row_out, cudaStream_t stream)
 {
     write_data_kernel<<<(N + 255) / 256, 256, 0, stream>>>(pwr, N, repeats_done, tuned_freq, samplerate, linear,
-                                                           baseline, freq_out, val_out);
+                                                           baseline, freq_out, val_out, row_out);
     return cudaGetLastError();
 }

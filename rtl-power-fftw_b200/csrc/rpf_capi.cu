@@ -1,14 +1,18 @@
 // rpf_capi.cu -- the C ABI of include/rpf_b200.h: context lifetime, the
 // continuous-stream bookkeeping of Datastore::fftThread (reference
-// src/datastore.cxx:48-96: fft_pointer carry-over, repeats limit, truncation)
-// and the host->device staging pipeline.  All arithmetic happens in the CUDA
-// kernels; there is no CPU fallback -- without a usable CUDA device every
-// compute entry point fails with RPF_ERR_CUDA.
+// src/datastore.cxx:48-96: fft_pointer carry-over, repeats limit, truncation),
+// the host->device staging pipeline, the dealing of whole spectra over the
+// context's GPUs and the final NCCL allreduce of pwr[].  All arithmetic happens
+// in the CUDA kernels; there is no CPU fallback -- without a usable CUDA device
+// every compute entry point fails with RPF_ERR_CUDA.
+#include <dlfcn.h>
 #include <math.h>
+#include <nccl.h>          // types and enums only: the library is dlopen()ed, see NcclApi
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <new>
 #include <vector>
 
 #include "../../include/rpf_b200.h"
@@ -17,42 +21,103 @@
 
 namespace {
 
-constexpr int kNumStage = 3;          // staging buffers in flight (copy / compute overlap)
-constexpr int kInnerN = 4096;         // inner transform length of the four-step path
+constexpr int kNumStage = 3;               // staging buffers in flight per device (copy / compute overlap)
+constexpr int kInnerN = 4096;              // inner transform length of the four-step path
+constexpr size_t kSmallPush = 256 << 10;   // pushes up to this size go through a pinned bounce buffer (no host wait)
+constexpr size_t kMinPartBytes = 1 << 20;  // a push is split over the devices only in parts of at least this size
 
 enum PlanKind { PLAN_SMALL, PLAN_FUSED3, PLAN_FOURSTEP, PLAN_DIRECT };
 
 thread_local char g_create_err[256] = "";
 
-}  // namespace
+// ---- NCCL, resolved at run time ------------------------------------------------------------------
+// Single-GPU use must not require libnccl, and a process that already carries an NCCL (PyTorch bundles
+// its own) must not get a second copy: the already loaded library is preferred (RTLD_NOLOAD), then the
+// system one.  Only the handful of entry points SURVEY.md 8(e) needs.
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
 
-struct rpf_ctx {
-    int N = 0, device = 0;
-    PlanKind plan = PLAN_SMALL;
-    int M = 1;                        // four-step outer radix
-    int grid = 0, groups = 1, nrows = 0;
-    int64_t rowlen = 0;               // doubles per private accumulator row
-    size_t spectrum_bytes = 0;        // 2N
-    bool has_window = false;
-    bool usepipe = false;             // N=4096 (and the four-step inner transform): pipe4096_kernel
+NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.ok ? &api : nullptr;
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return nullptr;
+    api.handle = h;
+    bool all = true;
+    auto sym = [&](const char *name) { void *p = dlsym(h, name); if (!p) all = false; return p; };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.ok = all;
+    return api.ok ? &api : nullptr;
+}
 
+// Everything that lives on one GPU.
+struct rpf_dev {
+    int device = 0, sms = 0;
+    int grid = 0, nrows = 0;
+    int rows_dirty = 0;               // private accumulator rows written since the last reset
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[kNumStage] = {}, ev_consumed[kNumStage] = {};
     uint8_t *d_stage[kNumStage] = {};
+    uint8_t *h_bounce[kNumStage] = {};   // pinned, kSmallPush + 2N bytes each
     size_t stage_cap = 0;
     int slot = 0;
-    uint8_t *h_carry[kNumStage] = {};   // pinned; carry for push k lives in h_carry[slot]
-    size_t carry_bytes = 0;
-
     float2 *d_twiddle = nullptr;      // W_Ni^j, Ni = inner N
     float2 *d_twiddle_big = nullptr;  // four-step: W_N^j
     float *d_window = nullptr;
     double *d_rows = nullptr, *d_pwr = nullptr, *d_tmp = nullptr, *d_baseline = nullptr;
     float2 *d_scratch = nullptr;
+    ncclComm_t comm = nullptr;
+    int64_t launches = 0;
+};
+
+}  // namespace
+
+struct rpf_ctx {
+    int N = 0;
+    PlanKind plan = PLAN_SMALL;
+    int M = 1;                        // four-step outer radix
+    int groups = 1;
+    int64_t rowlen = 0;               // doubles per private accumulator row
+    size_t spectrum_bytes = 0;        // 2N
+    bool has_window = false;
+    bool usepipe = false;             // N=4096 (and the four-step inner transform): pipe4096_kernel
+    bool use_tc = false;              // RPF_FLAG_TC_PASS1 and N=4096 without window: pipe4096_tc_kernel
+    bool pipelined = false;           // RPF_FLAG_PIPELINED_PUSH
     int64_t scratch_spectra = 0;
 
+    std::vector<rpf_dev> devs;        // devs[0] is the primary: results are read from it
+    int cursor = 0;                   // next device of the round-robin
+    int comm_rank = 0, comm_nranks = 1;   // multi-process communicator (rpf_comm_init_rank); 1 = none
+
+    uint8_t *h_carry[kNumStage] = {};   // pinned; the partial spectrum kept for the next push
+    int cslot = 0;
+    size_t carry_bytes = 0;
+    struct Pending { int dev, slot; };
+    std::vector<Pending> pending;     // host->device copies of the last push that were not waited for yet
+
     int64_t repeats = INT64_MAX, repeats_done = 0;
-    int64_t launches = 0;
     char err[256] = "";
 };
 
@@ -76,6 +141,14 @@ int fail(rpf_ctx *c, int code, const char *fmt, ...)
                         __FILE__, __LINE__);                                                          \
     } while (0)
 
+#define NC(c, api, call)                                                                              \
+    do {                                                                                              \
+        ncclResult_t r_ = (call);                                                                     \
+        if (r_ != ncclSuccess)                                                                        \
+            return fail((c), RPF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, (api)->GetErrorString(r_), \
+                        __FILE__, __LINE__);                                                          \
+    } while (0)
+
 bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
 
 void fill_twiddle(std::vector<float2> &t, int n)
@@ -90,50 +163,202 @@ void fill_twiddle(std::vector<float2> &t, int n)
     }
 }
 
-int ensure_stage(rpf_ctx *c, size_t need)
+int ensure_stage(rpf_ctx *c, rpf_dev &d, size_t need)
 {
-    if (need <= c->stage_cap) return RPF_OK;
-    CU(c, cudaStreamSynchronize(c->stream));
-    CU(c, cudaStreamSynchronize(c->copy_stream));
-    size_t cap = c->stage_cap ? c->stage_cap : (size_t)1 << 20;
+    if (need <= d.stage_cap) return RPF_OK;
+    CU(c, cudaStreamSynchronize(d.stream));
+    CU(c, cudaStreamSynchronize(d.copy_stream));
+    size_t cap = d.stage_cap ? d.stage_cap : (size_t)1 << 20;
     while (cap < need) cap *= 2;
     for (int i = 0; i < kNumStage; i++) {
-        if (c->d_stage[i]) CU(c, cudaFree(c->d_stage[i]));
-        c->d_stage[i] = nullptr;
-        CU(c, cudaMalloc(&c->d_stage[i], cap));
+        if (d.d_stage[i]) CU(c, cudaFree(d.d_stage[i]));
+        d.d_stage[i] = nullptr;
+        CU(c, cudaMalloc(&d.d_stage[i], cap));
     }
-    c->stage_cap = cap;
+    d.stage_cap = cap;
     return RPF_OK;
 }
 
+// Private accumulator rows a launch over `nspec` spectra writes (rows [0, result) of d_rows).
+int rows_touched(const rpf_ctx *c, const rpf_dev &d, int64_t nspec)
+{
+    int64_t blocks;
+    switch (c->plan) {
+        case PLAN_FUSED3:
+            blocks = c->usepipe ? (nspec + 1) / 2 : (nspec + c->groups - 1) / c->groups;
+            break;
+        case PLAN_FOURSTEP: return d.nrows;
+        default: blocks = nspec;
+    }
+    if (blocks > d.grid) blocks = d.grid;
+    return (int)blocks * c->groups;
+}
+
 // Enqueue the FFT work for `nspec` whole spectra starting at the 16-byte
-// aligned device pointer `src` on the compute stream.
-int launch_spectra(rpf_ctx *c, const uint8_t *src, int64_t nspec)
+// aligned device pointer `src` on the device's compute stream.
+int launch_spectra(rpf_ctx *c, rpf_dev &d, const uint8_t *src, int64_t nspec)
 {
     if (nspec <= 0) return RPF_OK;
     RpfLaunch L;
     L.bytes = src; L.cplx = nullptr; L.nspec = nspec; L.M = 1;
-    L.twiddle = c->d_twiddle; L.window = c->d_window; L.rows = c->d_rows;
-    L.grid = c->grid; L.stream = c->stream;
+    L.twiddle = d.d_twiddle; L.window = d.d_window; L.rows = d.d_rows;
+    L.grid = d.grid; L.stream = d.stream;
     if (c->plan == PLAN_FUSED3) {
-        CU(c, c->usepipe ? rpf_launch_pipe4096(L) : rpf_launch_fused3(c->N, L));
-        c->launches++;
+        CU(c, c->use_tc ? rpf_launch_pipe4096_tc(L) : c->usepipe ? rpf_launch_pipe4096(L) : rpf_launch_fused3(c->N, L));
+        d.launches++;
     } else if (c->plan == PLAN_SMALL) {
         CU(c, rpf_launch_small(c->N, L));
-        c->launches++;
+        d.launches++;
     } else if (c->plan == PLAN_DIRECT) {
         CU(c, rpf_launch_direct_dft(c->N, L));
-        c->launches++;
+        d.launches++;
     } else {
         for (int64_t done = 0; done < nspec; done += c->scratch_spectra) {
             const int64_t b = (nspec - done) < c->scratch_spectra ? (nspec - done) : c->scratch_spectra;
-            CU(c, rpf_launch_fourstep_outer(c->M, src + (size_t)done * c->spectrum_bytes, b, c->d_twiddle_big,
-                                            c->d_window, c->d_scratch, c->stream));
+            CU(c, rpf_launch_fourstep_outer(c->M, src + (size_t)done * c->spectrum_bytes, b, d.d_twiddle_big,
+                                            d.d_window, d.d_scratch, d.sms, d.stream));
             RpfLaunch Li = L;
-            Li.bytes = nullptr; Li.cplx = c->d_scratch; Li.nspec = b; Li.M = c->M; Li.window = nullptr;
+            Li.bytes = nullptr; Li.cplx = d.d_scratch; Li.nspec = b; Li.M = c->M; Li.window = nullptr;
             CU(c, rpf_launch_pipe4096(Li));
-            c->launches += 2;
+            d.launches += 2;
         }
+    }
+    const int r = rows_touched(c, d, nspec);
+    if (r > d.rows_dirty) d.rows_dirty = r;
+    return RPF_OK;
+}
+
+// The copies of an earlier push that the caller was not made to wait for.
+int drain_pending(rpf_ctx *c)
+{
+    for (const rpf_ctx::Pending &p : c->pending) {
+        CU(c, cudaSetDevice(c->devs[p.dev].device));
+        CU(c, cudaEventSynchronize(c->devs[p.dev].ev_copied[p.slot]));
+    }
+    c->pending.clear();
+    return RPF_OK;
+}
+
+int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
+{
+    const int N = c->N;
+    CU(c, cudaSetDevice(d.device));
+    CU(c, cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.device));
+    CU(c, cudaStreamCreateWithFlags(&d.own_stream, cudaStreamNonBlocking));
+    CU(c, cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+    d.stream = d.own_stream;
+    for (int i = 0; i < kNumStage; i++) {
+        CU(c, cudaEventCreateWithFlags(&d.ev_copied[i], cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&d.ev_consumed[i], cudaEventDisableTiming));
+        CU(c, cudaHostAlloc((void **)&d.h_bounce[i], kSmallPush + c->spectrum_bytes, cudaHostAllocDefault));
+    }
+    const int sms = d.sms;
+    int inner = N;
+    switch (c->plan) {
+        case PLAN_DIRECT:
+            d.grid = 4 * sms;
+            CU(c, rpf_direct_dft_configure());
+            break;
+        case PLAN_FUSED3:
+            d.grid = c->usepipe ? sms : 2 * sms;
+            break;
+        case PLAN_SMALL:
+            d.grid = 8 * sms;
+            break;
+        case PLAN_FOURSTEP: {
+            // inner transform = pipe4096 in complex-source mode: every CTA is bound to one outer bin, so the
+            // grid is a multiple of M (CTAs are persistent; co-residency is not required for correctness)
+            inner = kInnerN;
+            d.grid = (sms / c->M) * c->M;
+            if (d.grid < c->M) d.grid = c->M;
+            CU(c, cudaMalloc(&d.d_scratch, (size_t)c->scratch_spectra * N * sizeof(float2)));
+            std::vector<float2> tb;
+            fill_twiddle(tb, N);
+            CU(c, cudaMalloc(&d.d_twiddle_big, sizeof(float2) * N));
+            CU(c, cudaMemcpy(d.d_twiddle_big, tb.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+            break;
+        }
+    }
+    if (c->plan == PLAN_FUSED3 || c->plan == PLAN_FOURSTEP) {
+        CU(c, rpf_fused3_configure());
+        CU(c, rpf_pipe4096_configure());
+        if (c->use_tc) CU(c, rpf_pipe4096_tc_configure());
+    }
+    std::vector<float2> tw;
+    fill_twiddle(tw, inner);
+    CU(c, cudaMalloc(&d.d_twiddle, sizeof(float2) * inner));
+    CU(c, cudaMemcpy(d.d_twiddle, tw.data(), sizeof(float2) * inner, cudaMemcpyHostToDevice));
+    if (cfg->window) {
+        CU(c, cudaMalloc(&d.d_window, sizeof(float) * N));
+        CU(c, cudaMemcpy(d.d_window, cfg->window, sizeof(float) * N, cudaMemcpyHostToDevice));
+    }
+    d.nrows = d.grid * c->groups;
+    CU(c, cudaMalloc(&d.d_rows, sizeof(double) * (size_t)d.nrows * c->rowlen));
+    CU(c, cudaMalloc(&d.d_pwr, sizeof(double) * N));
+    CU(c, cudaMalloc(&d.d_tmp, sizeof(double) * 2 * N));
+    CU(c, cudaMalloc(&d.d_baseline, sizeof(double) * N));
+    CU(c, cudaMemset(d.d_rows, 0, sizeof(double) * (size_t)d.nrows * c->rowlen));
+    d.rows_dirty = 0;
+    const size_t hint = cfg->buf_length > 0 ? (size_t)cfg->buf_length : (size_t)16384 * 100;   // src/params.h:43
+    const int r = ensure_stage(c, d, hint + c->spectrum_bytes);
+    if (r) return r;
+    CU(c, cudaDeviceSynchronize());
+    return RPF_OK;
+}
+
+// pwr[] of one device (sum of its private rows, fixed order) into `out` (device memory), on its stream.
+int reduce_device(rpf_ctx *c, rpf_dev &d, double *out)
+{
+    if (d.rows_dirty == 0) {
+        CU(c, cudaMemsetAsync(out, 0, sizeof(double) * c->N, d.stream));
+        return RPF_OK;
+    }
+    if (c->plan == PLAN_FOURSTEP)
+        CU(c, rpf_launch_reduce_rows_fourstep(d.d_rows, d.rows_dirty, c->M, kInnerN, out, d.stream));
+    else
+        CU(c, rpf_launch_reduce_rows(d.d_rows, d.rows_dirty, c->N, out, d.stream));
+    d.launches++;
+    return RPF_OK;
+}
+
+// Sum of Datastore::pwr over every GPU of the context and every rank of the communicator
+// (src/datastore.cxx:83-85 is a sum, so the order of spectra does not matter): reduce on each device,
+// then ONE ncclAllReduce of N doubles per communicator, enqueued on the compute streams.
+// Once devs[0].stream has drained, devs[0].d_pwr (or `out0` if given) holds the total.
+int reduce_all(rpf_ctx *c, double *out0)
+{
+    NcclApi *api = nullptr;
+    if (c->devs.size() > 1 || c->comm_nranks > 1) {
+        api = nccl_api();
+        if (!api) return fail(c, RPF_ERR_STATE, "multi-GPU reduction needs libnccl.so.2 (not found)");
+    }
+    for (size_t i = 0; i < c->devs.size(); i++) {
+        rpf_dev &d = c->devs[i];
+        CU(c, cudaSetDevice(d.device));
+        int r = reduce_device(c, d, (i == 0 && out0) ? out0 : d.d_pwr);
+        if (r) return r;
+    }
+    if (c->devs.size() > 1) {
+        NC(c, api, api->GroupStart());
+        for (size_t i = 0; i < c->devs.size(); i++) {
+            rpf_dev &d = c->devs[i];
+            double *buf = (i == 0 && out0) ? out0 : d.d_pwr;
+            NC(c, api, api->AllReduce(buf, buf, (size_t)c->N, ncclDouble, ncclSum, d.comm, d.stream));
+        }
+        NC(c, api, api->GroupEnd());
+    } else if (c->comm_nranks > 1) {
+        rpf_dev &d = c->devs[0];
+        double *buf = out0 ? out0 : d.d_pwr;
+        NC(c, api, api->AllReduce(buf, buf, (size_t)c->N, ncclDouble, ncclSum, d.comm, d.stream));
+    }
+    return RPF_OK;
+}
+
+int sync_compute_streams(rpf_ctx *c)
+{
+    for (rpf_dev &d : c->devs) {
+        CU(c, cudaSetDevice(d.device));
+        CU(c, cudaStreamSynchronize(d.stream));
     }
     return RPF_OK;
 }
@@ -158,85 +383,67 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
                     "rpf_create: N=%d not supported by the CUDA path (powers of two up to 65536, other even N up to 8190)", N);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0)
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
         return fail(nullptr, RPF_ERR_CUDA, "rpf_create: no usable CUDA device (%s); there is no CPU fallback",
                     cudaGetErrorString(e));
-    if (cfg->device < 0 || cfg->device >= ndev)
-        return fail(nullptr, RPF_ERR_INVALID_ARG, "rpf_create: device %d out of range [0,%d)", cfg->device, ndev);
+    }
+    const int nd = cfg->n_devices > 0 ? cfg->n_devices : 1;
+    if (nd > RPF_MAX_DEVICES)
+        return fail(nullptr, RPF_ERR_INVALID_ARG, "rpf_create: n_devices %d > %d", nd, RPF_MAX_DEVICES);
+    for (int i = 0; i < nd; i++) {
+        const int dv = cfg->n_devices > 0 ? cfg->devices[i] : cfg->device;
+        if (dv < 0 || dv >= ndev)
+            return fail(nullptr, RPF_ERR_INVALID_ARG, "rpf_create: device %d out of range [0,%d)", dv, ndev);
+        for (int k = 0; k < i; k++)
+            if (cfg->devices[k] == dv) return fail(nullptr, RPF_ERR_INVALID_ARG, "rpf_create: device %d listed twice", dv);
+    }
 
     rpf_ctx *c = new (std::nothrow) rpf_ctx;
     if (!c) return fail(nullptr, RPF_ERR_NOMEM, "rpf_create: out of host memory");
-    c->N = N; c->device = cfg->device;
+    c->N = N;
     c->spectrum_bytes = (size_t)2 * N;
     c->has_window = cfg->window != nullptr;
-    int rc = RPF_OK;
+    c->pipelined = (cfg->flags & RPF_FLAG_PIPELINED_PUSH) != 0;
     auto body = [&]() -> int {
-        CU(c, cudaSetDevice(c->device));
-        int sms = 0;
-        CU(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-        CU(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-        CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        c->stream = c->own_stream;
-        for (int i = 0; i < kNumStage; i++) {
-            CU(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
-            CU(c, cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
-            CU(c, cudaHostAlloc((void **)&c->h_carry[i], c->spectrum_bytes, cudaHostAllocDefault));
-        }
-        int inner = N;
-        // development A/B switch only: RPF_B200_KERNEL=generic runs N=4096 on the generic 3-pass kernel
-        const char *kname = getenv("RPF_B200_KERNEL");
-        const bool generic = kname && !strcmp(kname, "generic");
         if (!is_pow2(N)) {
-            c->plan = PLAN_DIRECT; c->groups = 1; c->grid = 4 * sms;
-            CU(c, rpf_direct_dft_configure());
+            c->plan = PLAN_DIRECT; c->groups = 1;
         } else if (rpf_fused3_supported(N)) {
             c->plan = PLAN_FUSED3;
-            c->usepipe = (N == kInnerN) && !generic;
+            c->usepipe = (N == kInnerN);
+            c->use_tc = c->usepipe && !cfg->window && (cfg->flags & RPF_FLAG_TC_PASS1);
             c->groups = c->usepipe ? 1 : rpf_fused3_groups(N);
-            c->grid = c->usepipe ? sms : 2 * sms;
         } else if (N <= 256) {
-            c->plan = PLAN_SMALL; c->groups = 1; c->grid = 8 * sms;
+            c->plan = PLAN_SMALL; c->groups = 1;
         } else {
-            // inner transform = pipe4096 in complex-source mode: every CTA is bound to one outer bin
-            c->plan = PLAN_FOURSTEP; c->M = N / kInnerN; inner = kInnerN;
+            c->plan = PLAN_FOURSTEP; c->M = N / kInnerN;
             c->usepipe = true; c->groups = 1;
-            c->grid = (sms / c->M) * c->M;
-            size_t scratch_mb = 256;                                  // batch of complex64 rows (measured: 64 -> 171, 256 -> 205 Gs/s)
-            if (const char *e = getenv("RPF_B200_SCRATCH_MB")) scratch_mb = (size_t)atoi(e) > 0 ? (size_t)atoi(e) : 256;
+            const size_t scratch_mb = 256;                            // batch of complex64 rows (measured: 64 -> 171, 256 -> 205 Gs/s)
             c->scratch_spectra = (scratch_mb << 20) / ((size_t)N * sizeof(float2));
             if (c->scratch_spectra < 1) c->scratch_spectra = 1;
-            CU(c, cudaMalloc(&c->d_scratch, (size_t)c->scratch_spectra * N * sizeof(float2)));
-            std::vector<float2> tb;
-            fill_twiddle(tb, N);
-            CU(c, cudaMalloc(&c->d_twiddle_big, sizeof(float2) * N));
-            CU(c, cudaMemcpy(c->d_twiddle_big, tb.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
         }
-        if (c->plan != PLAN_SMALL && c->plan != PLAN_DIRECT) {
-            CU(c, rpf_fused3_configure());
-            CU(c, rpf_pipe4096_configure());
-        }
-        std::vector<float2> tw;
-        fill_twiddle(tw, inner);
-        CU(c, cudaMalloc(&c->d_twiddle, sizeof(float2) * inner));
-        CU(c, cudaMemcpy(c->d_twiddle, tw.data(), sizeof(float2) * inner, cudaMemcpyHostToDevice));
-        if (cfg->window) {
-            CU(c, cudaMalloc(&c->d_window, sizeof(float) * N));
-            CU(c, cudaMemcpy(c->d_window, cfg->window, sizeof(float) * N, cudaMemcpyHostToDevice));
-        }
-        c->nrows = c->grid * c->groups;
         c->rowlen = c->plan == PLAN_FOURSTEP ? kInnerN : N;
-        CU(c, cudaMalloc(&c->d_rows, sizeof(double) * (size_t)c->nrows * c->rowlen));
-        CU(c, cudaMalloc(&c->d_pwr, sizeof(double) * N));
-        CU(c, cudaMalloc(&c->d_tmp, sizeof(double) * 2 * N));
-        CU(c, cudaMalloc(&c->d_baseline, sizeof(double) * N));
-        CU(c, cudaMemset(c->d_rows, 0, sizeof(double) * (size_t)c->nrows * c->rowlen));
-        size_t hint = cfg->buf_length > 0 ? (size_t)cfg->buf_length : (size_t)16384 * 100;   // src/params.h:43
-        int r = ensure_stage(c, hint + c->spectrum_bytes);
-        if (r) return r;
-        CU(c, cudaDeviceSynchronize());
+        c->devs.resize(nd);
+        for (int i = 0; i < nd; i++) {
+            c->devs[i].device = cfg->n_devices > 0 ? cfg->devices[i] : cfg->device;
+            int r = create_device(c, c->devs[i], cfg);
+            if (r) return r;
+        }
+        for (int i = 0; i < kNumStage; i++)
+            CU(c, cudaHostAlloc((void **)&c->h_carry[i], c->spectrum_bytes, cudaHostAllocDefault));
+        if (nd > 1) {
+            // single process, ncclCommInitAll over the context's devices
+            NcclApi *api = nccl_api();
+            if (!api) return fail(c, RPF_ERR_STATE, "rpf_create: n_devices > 1 needs libnccl.so.2 (not found)");
+            std::vector<ncclComm_t> comms(nd);
+            std::vector<int> ids(nd);
+            for (int i = 0; i < nd; i++) ids[i] = c->devs[i].device;
+            NC(c, api, api->CommInitAll(comms.data(), nd, ids.data()));
+            for (int i = 0; i < nd; i++) c->devs[i].comm = comms[i];
+        }
         return RPF_OK;
     };
-    rc = body();
+    const int rc = body();
     if (rc != RPF_OK) {
         snprintf(g_create_err, sizeof(g_create_err), "%s", c->err);
         rpf_destroy(c);
@@ -249,19 +456,26 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
 void rpf_destroy(rpf_ctx *c)
 {
     if (!c) return;
-    cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    for (int i = 0; i < kNumStage; i++) {
-        if (c->d_stage[i]) cudaFree(c->d_stage[i]);
-        if (c->h_carry[i]) cudaFreeHost(c->h_carry[i]);
-        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
-        if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
+    NcclApi *api = nccl_api();
+    for (rpf_dev &d : c->devs) {
+        cudaSetDevice(d.device);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        if (d.copy_stream) cudaStreamSynchronize(d.copy_stream);
+        if (d.comm && api) api->CommDestroy(d.comm);
+        for (int i = 0; i < kNumStage; i++) {
+            if (d.d_stage[i]) cudaFree(d.d_stage[i]);
+            if (d.h_bounce[i]) cudaFreeHost(d.h_bounce[i]);
+            if (d.ev_copied[i]) cudaEventDestroy(d.ev_copied[i]);
+            if (d.ev_consumed[i]) cudaEventDestroy(d.ev_consumed[i]);
+        }
+        cudaFree(d.d_twiddle); cudaFree(d.d_twiddle_big); cudaFree(d.d_window);
+        cudaFree(d.d_rows); cudaFree(d.d_pwr); cudaFree(d.d_tmp); cudaFree(d.d_baseline); cudaFree(d.d_scratch);
+        if (d.own_stream) cudaStreamDestroy(d.own_stream);
+        if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     }
-    cudaFree(c->d_twiddle); cudaFree(c->d_twiddle_big); cudaFree(c->d_window);
-    cudaFree(c->d_rows); cudaFree(c->d_pwr); cudaFree(c->d_tmp); cudaFree(c->d_baseline); cudaFree(c->d_scratch);
-    if (c->own_stream) cudaStreamDestroy(c->own_stream);
-    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < kNumStage; i++)
+        if (c->h_carry[i]) cudaFreeHost(c->h_carry[i]);
+    cudaGetLastError();
     delete c;
 }
 
@@ -269,8 +483,14 @@ int rpf_reset(rpf_ctx *c, int64_t repeats)
 {
     if (!c) return RPF_ERR_INVALID_ARG;
     if (repeats < 0) return fail(c, RPF_ERR_INVALID_ARG, "rpf_reset: repeats must be >= 0");
-    CU(c, cudaSetDevice(c->device));
-    CU(c, cudaMemsetAsync(c->d_rows, 0, sizeof(double) * (size_t)c->nrows * c->rowlen, c->stream));
+    int r = drain_pending(c);
+    if (r) return r;
+    for (rpf_dev &d : c->devs) {
+        CU(c, cudaSetDevice(d.device));
+        if (d.rows_dirty)   // only the rows a launch wrote since the last reset
+            CU(c, cudaMemsetAsync(d.d_rows, 0, sizeof(double) * (size_t)d.rows_dirty * c->rowlen, d.stream));
+        d.rows_dirty = 0;
+    }
     c->repeats = repeats;
     c->repeats_done = 0;
     c->carry_bytes = 0;
@@ -283,47 +503,84 @@ int rpf_push(rpf_ctx *c, const uint8_t *bytes, size_t len)
     if (len == 0) return RPF_OK;
     if (!bytes) return fail(c, RPF_ERR_INVALID_ARG, "rpf_push: NULL buffer");
     if (len & 1) return fail(c, RPF_ERR_INVALID_ARG, "rpf_push: odd byte count %zu (I/Q pairs, src/datastore.cxx:74)", len);
-    if (c->repeats_done >= c->repeats) return RPF_OK;          // src/datastore.cxx:67: discarded
-    CU(c, cudaSetDevice(c->device));
+    int r = drain_pending(c);                                    // pipelined mode: the previous push's copies
+    if (r) return r;
+    if (c->repeats_done >= c->repeats) return RPF_OK;            // src/datastore.cxx:67: discarded
 
     const size_t sb = c->spectrum_bytes;
     const size_t total = c->carry_bytes + len;
-    const int s = c->slot, sn = (c->slot + 1) % kNumStage;
+    const int cs = c->cslot, cn = (c->cslot + 1) % kNumStage;
     if (total < sb) {                                            // still inside one spectrum
-        memcpy(c->h_carry[sn], c->h_carry[s], c->carry_bytes);
-        memcpy(c->h_carry[sn] + c->carry_bytes, bytes, len);
+        memcpy(c->h_carry[cn], c->h_carry[cs], c->carry_bytes);
+        memcpy(c->h_carry[cn] + c->carry_bytes, bytes, len);
         c->carry_bytes = total;
-        c->slot = sn;
+        c->cslot = cn;
         return RPF_OK;
     }
-    int r = ensure_stage(c, total);
-    if (r) return r;
     const int64_t avail = (int64_t)(total / sb);
     const int64_t left = c->repeats - c->repeats_done;
     const int64_t nspec = avail < left ? avail : left;
-    const size_t used = (size_t)nspec * sb;                      // bytes the kernels will read
-    // copy stream: wait until the kernels that last read this staging buffer are done
-    CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[s], 0));
-    if (c->carry_bytes)
-        CU(c, cudaMemcpyAsync(c->d_stage[s], c->h_carry[s], c->carry_bytes, cudaMemcpyHostToDevice, c->copy_stream));
-    const size_t copy_new = used - c->carry_bytes < len ? used - c->carry_bytes : len;
-    CU(c, cudaMemcpyAsync(c->d_stage[s] + c->carry_bytes, bytes, copy_new, cudaMemcpyHostToDevice, c->copy_stream));
-    CU(c, cudaEventRecord(c->ev_copied[s], c->copy_stream));
-    CU(c, cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
-    r = launch_spectra(c, c->d_stage[s], nspec);
-    if (r) return r;
-    CU(c, cudaEventRecord(c->ev_consumed[s], c->stream));
+    const size_t used = (size_t)nspec * sb;                      // carry + new bytes the kernels will read
+
+    // Deal the whole spectra of this push over the GPUs: contiguous parts of at least kMinPartBytes, starting at
+    // the round-robin cursor (small pushes therefore go to one GPU each, in turn).  The carry was resolved above,
+    // once, before dealing: every part starts on a spectrum boundary.
+    const int nd = (int)c->devs.size();
+    int parts = (int)(used / kMinPartBytes);
+    if (parts < 1) parts = 1;
+    if (parts > nd) parts = nd;
+    if ((int64_t)parts > nspec) parts = (int)nspec;
+    size_t consumed = 0;                                         // bytes of (carry + new) dealt so far
+    for (int p = 0; p < parts; p++) {
+        const int64_t s0 = nspec * p / parts, s1 = nspec * (p + 1) / parts;
+        const size_t part_bytes = (size_t)(s1 - s0) * sb;
+        const int di = (c->cursor + p) % nd;
+        rpf_dev &d = c->devs[di];
+        CU(c, cudaSetDevice(d.device));
+        r = ensure_stage(c, d, part_bytes);
+        if (r) return r;
+        const int s = d.slot;
+        d.slot = (d.slot + 1) % kNumStage;
+        const size_t from_carry = consumed < c->carry_bytes ? c->carry_bytes - consumed : 0;   // only part 0
+        const uint8_t *src = bytes + (consumed + from_carry - c->carry_bytes);
+        const size_t from_new = part_bytes - from_carry;
+        if (part_bytes <= kSmallPush + sb && !c->pipelined) {
+            // short read (config 1: one 114,688-byte buffer): bounce through pinned memory on the compute stream;
+            // the caller's buffer is free as soon as the host memcpy returns, nobody waits for an event
+            CU(c, cudaEventSynchronize(d.ev_consumed[s]));       // bounce slot free (3 pushes ago)
+            if (from_carry) memcpy(d.h_bounce[s], c->h_carry[cs], from_carry);
+            memcpy(d.h_bounce[s] + from_carry, src, from_new);
+            CU(c, cudaMemcpyAsync(d.d_stage[s], d.h_bounce[s], part_bytes, cudaMemcpyHostToDevice, d.stream));
+            r = launch_spectra(c, d, d.d_stage[s], s1 - s0);
+            if (r) return r;
+            CU(c, cudaEventRecord(d.ev_consumed[s], d.stream));
+        } else {
+            // copy stream: wait until the kernels that last read this staging buffer are done
+            CU(c, cudaStreamWaitEvent(d.copy_stream, d.ev_consumed[s], 0));
+            if (from_carry)
+                CU(c, cudaMemcpyAsync(d.d_stage[s], c->h_carry[cs], from_carry, cudaMemcpyHostToDevice, d.copy_stream));
+            CU(c, cudaMemcpyAsync(d.d_stage[s] + from_carry, src, from_new, cudaMemcpyHostToDevice, d.copy_stream));
+            CU(c, cudaEventRecord(d.ev_copied[s], d.copy_stream));
+            CU(c, cudaStreamWaitEvent(d.stream, d.ev_copied[s], 0));
+            r = launch_spectra(c, d, d.d_stage[s], s1 - s0);
+            if (r) return r;
+            CU(c, cudaEventRecord(d.ev_consumed[s], d.stream));
+            c->pending.push_back({di, s});
+        }
+        consumed += part_bytes;
+    }
+    c->cursor = (c->cursor + parts) % nd;
     c->repeats_done += nspec;
     if (c->repeats_done >= c->repeats) {
         c->carry_bytes = 0;                                      // rest of the stream is discarded
     } else {
         const size_t tail = total - used;                        // < sb; lies entirely in `bytes`
-        memcpy(c->h_carry[sn], bytes + (len - tail), tail);
+        memcpy(c->h_carry[cn], bytes + (len - tail), tail);
         c->carry_bytes = tail;
     }
-    c->slot = sn;
-    CU(c, cudaEventSynchronize(c->ev_copied[s]));                // caller may now reuse `bytes`
-    return RPF_OK;
+    c->cslot = cn;
+    if (!c->pipelined) return drain_pending(c);                  // caller may now reuse `bytes`
+    return RPF_OK;                                               // pipelined: `bytes` is free after the NEXT call
 }
 
 int rpf_push_device(rpf_ctx *c, const uint8_t *bytes, size_t len)
@@ -332,82 +589,99 @@ int rpf_push_device(rpf_ctx *c, const uint8_t *bytes, size_t len)
     if (len == 0) return RPF_OK;
     if (!bytes) return fail(c, RPF_ERR_INVALID_ARG, "rpf_push_device: NULL buffer");
     if (len & 1) return fail(c, RPF_ERR_INVALID_ARG, "rpf_push_device: odd byte count %zu", len);
+    int r = drain_pending(c);
+    if (r) return r;
     if (c->repeats_done >= c->repeats) return RPF_OK;
-    CU(c, cudaSetDevice(c->device));
     const size_t sb = c->spectrum_bytes;
     const int64_t left = c->repeats - c->repeats_done;
+
+    // which of the context's GPUs owns the buffer
+    int di = 0;
+    if (c->devs.size() > 1) {
+        cudaPointerAttributes at;
+        CU(c, cudaPointerGetAttributes(&at, bytes));
+        di = -1;
+        for (size_t i = 0; i < c->devs.size(); i++)
+            if (c->devs[i].device == at.device && at.type == cudaMemoryTypeDevice) di = (int)i;
+        if (di < 0) return fail(c, RPF_ERR_INVALID_ARG, "rpf_push_device: buffer is not in the memory of one of the context's GPUs");
+        if (c->carry_bytes || len % sb)
+            return fail(c, RPF_ERR_STATE, "rpf_push_device: with several GPUs device buffers must hold whole spectra "
+                                          "(no partial spectrum may be pending or left over)");
+    }
+    rpf_dev &d = c->devs[di];
+    CU(c, cudaSetDevice(d.device));
 
     if (c->carry_bytes == 0 && (((uintptr_t)bytes) & 15) == 0) {
         // zero-copy: spectra are read in place by TMA
         const int64_t avail = (int64_t)(len / sb);
         const int64_t nspec = avail < left ? avail : left;
-        int r = launch_spectra(c, bytes, nspec);
+        r = launch_spectra(c, d, bytes, nspec);
         if (r) return r;
         c->repeats_done += nspec;
         if (c->repeats_done >= c->repeats) return RPF_OK;
         const size_t tail = len - (size_t)nspec * sb;
         if (tail) {
-            const int sn = c->slot;
-            CU(c, cudaMemcpyAsync(c->h_carry[sn], bytes + (len - tail), tail, cudaMemcpyDeviceToHost, c->stream));
-            CU(c, cudaStreamSynchronize(c->stream));
+            CU(c, cudaMemcpyAsync(c->h_carry[c->cslot], bytes + (len - tail), tail, cudaMemcpyDeviceToHost, d.stream));
+            CU(c, cudaStreamSynchronize(d.stream));
             c->carry_bytes = tail;
         }
         return RPF_OK;
     }
     // general case: assemble carry + buffer contiguously in staging (device-to-device)
     const size_t total = c->carry_bytes + len;
-    const int s = c->slot, sn = (c->slot + 1) % kNumStage;
+    const int cs = c->cslot, cn = (c->cslot + 1) % kNumStage;
     if (total < sb) {
-        memcpy(c->h_carry[sn], c->h_carry[s], c->carry_bytes);
-        CU(c, cudaMemcpyAsync(c->h_carry[sn] + c->carry_bytes, bytes, len, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
-        c->carry_bytes = total; c->slot = sn;
+        memcpy(c->h_carry[cn], c->h_carry[cs], c->carry_bytes);
+        CU(c, cudaMemcpyAsync(c->h_carry[cn] + c->carry_bytes, bytes, len, cudaMemcpyDeviceToHost, d.stream));
+        CU(c, cudaStreamSynchronize(d.stream));
+        c->carry_bytes = total; c->cslot = cn;
         return RPF_OK;
     }
-    int r = ensure_stage(c, total);
+    r = ensure_stage(c, d, total);
     if (r) return r;
+    const int s = d.slot;
+    d.slot = (d.slot + 1) % kNumStage;
     const int64_t avail = (int64_t)(total / sb);
     const int64_t nspec = avail < left ? avail : left;
     const size_t used = (size_t)nspec * sb;
-    CU(c, cudaStreamWaitEvent(c->stream, c->ev_consumed[s], 0));
+    CU(c, cudaStreamWaitEvent(d.stream, d.ev_consumed[s], 0));
     if (c->carry_bytes)
-        CU(c, cudaMemcpyAsync(c->d_stage[s], c->h_carry[s], c->carry_bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->d_stage[s] + c->carry_bytes, bytes, used - c->carry_bytes, cudaMemcpyDeviceToDevice, c->stream));
-    r = launch_spectra(c, c->d_stage[s], nspec);
+        CU(c, cudaMemcpyAsync(d.d_stage[s], c->h_carry[cs], c->carry_bytes, cudaMemcpyHostToDevice, d.stream));
+    CU(c, cudaMemcpyAsync(d.d_stage[s] + c->carry_bytes, bytes, used - c->carry_bytes, cudaMemcpyDeviceToDevice, d.stream));
+    r = launch_spectra(c, d, d.d_stage[s], nspec);
     if (r) return r;
-    CU(c, cudaEventRecord(c->ev_consumed[s], c->stream));
+    CU(c, cudaEventRecord(d.ev_consumed[s], d.stream));
     c->repeats_done += nspec;
-    if (c->repeats_done >= c->repeats) {
-        c->carry_bytes = 0;
-    } else {
-        const size_t tail = total - used;
-        if (tail) CU(c, cudaMemcpyAsync(c->h_carry[sn], bytes + (len - tail), tail, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
-        c->carry_bytes = tail;
-    }
-    c->slot = sn;
+    const size_t tail = c->repeats_done >= c->repeats ? 0 : total - used;
+    if (tail) CU(c, cudaMemcpyAsync(c->h_carry[cn], bytes + (len - tail), tail, cudaMemcpyDeviceToHost, d.stream));
+    // in every branch: the pinned h_carry[cs] -> staging copy has completed before that slot can be rewritten
+    CU(c, cudaStreamSynchronize(d.stream));
+    c->carry_bytes = tail;
+    c->cslot = cn;
     return RPF_OK;
 }
 
 int rpf_sync(rpf_ctx *c)
 {
     if (!c) return RPF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
-    CU(c, cudaStreamSynchronize(c->copy_stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    int r = drain_pending(c);
+    if (r) return r;
+    for (rpf_dev &d : c->devs) {
+        CU(c, cudaSetDevice(d.device));
+        CU(c, cudaStreamSynchronize(d.copy_stream));
+        CU(c, cudaStreamSynchronize(d.stream));
+    }
     return RPF_OK;
 }
 
 int rpf_finish_device(rpf_ctx *c, double *pwr_out_device, int64_t *repeats_done)
 {
     if (!c) return RPF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    int r = drain_pending(c);
+    if (r) return r;
     if (pwr_out_device) {
-        if (c->plan == PLAN_FOURSTEP)
-            CU(c, rpf_launch_reduce_rows_fourstep(c->d_rows, c->nrows, c->M, kInnerN, pwr_out_device, c->stream));
-        else
-            CU(c, rpf_launch_reduce_rows(c->d_rows, c->nrows, c->N, pwr_out_device, c->stream));
-        c->launches++;
+        r = reduce_all(c, pwr_out_device);
+        if (r) return r;
     }
     if (repeats_done) *repeats_done = c->repeats_done;
     return RPF_OK;
@@ -416,31 +690,80 @@ int rpf_finish_device(rpf_ctx *c, double *pwr_out_device, int64_t *repeats_done)
 int rpf_finish(rpf_ctx *c, double *pwr_out, int64_t *repeats_done)
 {
     if (!c) return RPF_ERR_INVALID_ARG;
-    int r = rpf_finish_device(c, pwr_out ? c->d_pwr : nullptr, repeats_done);
+    int r = drain_pending(c);
     if (r) return r;
-    if (pwr_out)
-        CU(c, cudaMemcpyAsync(pwr_out, c->d_pwr, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    rpf_dev &d0 = c->devs[0];
+    if (pwr_out) {
+        r = reduce_all(c, nullptr);
+        if (r) return r;
+        CU(c, cudaSetDevice(d0.device));
+        CU(c, cudaMemcpyAsync(pwr_out, d0.d_pwr, sizeof(double) * c->N, cudaMemcpyDeviceToHost, d0.stream));
+    }
+    r = sync_compute_streams(c);
+    if (r) return r;
+    if (repeats_done) *repeats_done = c->repeats_done;
     return RPF_OK;
 }
 
 int64_t rpf_repeats_done(const rpf_ctx *c) { return c ? c->repeats_done : 0; }
 int64_t rpf_fft_pointer(const rpf_ctx *c) { return c ? (int64_t)(c->carry_bytes / 2) : 0; }
-int64_t rpf_kernel_launches(const rpf_ctx *c) { return c ? c->launches : 0; }
+int64_t rpf_kernel_launches(const rpf_ctx *c)
+{
+    int64_t n = 0;
+    if (c) for (const rpf_dev &d : c->devs) n += d.launches;
+    return n;
+}
+int32_t rpf_device_count(const rpf_ctx *c) { return c ? (int32_t)c->devs.size() : 0; }
 
 const char *rpf_plan_name(const rpf_ctx *c)
 {
     if (!c) return "";
+    if (c->use_tc) return "pipe4096_tc";
     return c->plan == PLAN_SMALL ? "small" : c->plan == PLAN_FUSED3 ? "fused3" : c->plan == PLAN_DIRECT ? "direct" : "fourstep";
 }
 
 int rpf_set_stream(rpf_ctx *c, void *cuda_stream)
 {
     if (!c) return RPF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
-    CU(c, cudaStreamSynchronize(c->stream));
-    CU(c, cudaStreamSynchronize(c->copy_stream));
-    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    if (c->devs.size() != 1) return fail(c, RPF_ERR_STATE, "rpf_set_stream: only for single-GPU contexts");
+    int r = drain_pending(c);
+    if (r) return r;
+    rpf_dev &d = c->devs[0];
+    CU(c, cudaSetDevice(d.device));
+    CU(c, cudaStreamSynchronize(d.stream));
+    CU(c, cudaStreamSynchronize(d.copy_stream));
+    d.stream = cuda_stream ? (cudaStream_t)cuda_stream : d.own_stream;
+    return RPF_OK;
+}
+
+int rpf_comm_unique_id(void *id_out, size_t id_bytes)
+{
+    NcclApi *api = nccl_api();
+    if (!api) return fail(nullptr, RPF_ERR_STATE, "rpf_comm_unique_id: libnccl.so.2 not found");
+    if (!id_out || id_bytes < sizeof(ncclUniqueId))
+        return fail(nullptr, RPF_ERR_INVALID_ARG, "rpf_comm_unique_id: need %zu bytes", sizeof(ncclUniqueId));
+    ncclUniqueId id;
+    if (api->GetUniqueId(&id) != ncclSuccess) return fail(nullptr, RPF_ERR_CUDA, "ncclGetUniqueId failed");
+    memcpy(id_out, &id, sizeof(id));
+    return RPF_OK;
+}
+
+int rpf_comm_init_rank(rpf_ctx *c, const void *id, size_t id_bytes, int32_t rank, int32_t nranks)
+{
+    if (!c || !id) return RPF_ERR_INVALID_ARG;
+    if (c->devs.size() != 1)
+        return fail(c, RPF_ERR_STATE, "rpf_comm_init_rank: the context already spans several GPUs (one communicator per context)");
+    if (id_bytes < sizeof(ncclUniqueId) || nranks < 1 || rank < 0 || rank >= nranks)
+        return fail(c, RPF_ERR_INVALID_ARG, "rpf_comm_init_rank: bad arguments");
+    NcclApi *api = nccl_api();
+    if (!api) return fail(c, RPF_ERR_STATE, "rpf_comm_init_rank: libnccl.so.2 not found");
+    rpf_dev &d = c->devs[0];
+    CU(c, cudaSetDevice(d.device));
+    if (d.comm) { api->CommDestroy(d.comm); d.comm = nullptr; }
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    NC(c, api, api->CommInitRank(&d.comm, nranks, uid, rank));
+    c->comm_rank = rank; c->comm_nranks = nranks;
     return RPF_OK;
 }
 
@@ -449,21 +772,42 @@ int rpf_write_data(rpf_ctx *c, double tuned_freq, int32_t samplerate, int32_t li
 {
     if (!c || !val_out) return RPF_ERR_INVALID_ARG;
     if (samplerate <= 0) return fail(c, RPF_ERR_INVALID_ARG, "rpf_write_data: samplerate must be > 0");
-    CU(c, cudaSetDevice(c->device));
+    int r = drain_pending(c);
+    if (r) return r;
+    r = reduce_all(c, nullptr);
+    if (r) return r;
+    rpf_dev &d = c->devs[0];
+    CU(c, cudaSetDevice(d.device));
     const int N = c->N;
-    if (c->plan == PLAN_FOURSTEP)
-        CU(c, rpf_launch_reduce_rows_fourstep(c->d_rows, c->nrows, c->M, kInnerN, c->d_pwr, c->stream));
-    else
-        CU(c, rpf_launch_reduce_rows(c->d_rows, c->nrows, N, c->d_pwr, c->stream));
     if (baseline)
-        CU(c, cudaMemcpyAsync(c->d_baseline, baseline, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
-    CU(c, rpf_launch_write_data(c->d_pwr, N, c->repeats_done, tuned_freq, samplerate, linear,
-                                baseline ? c->d_baseline : nullptr, c->d_tmp, c->d_tmp + N, c->stream));
-    c->launches += 2;
-    if (freq_out) CU(c, cudaMemcpyAsync(freq_out, c->d_tmp, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(val_out, c->d_tmp + N, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    return RPF_OK;
+        CU(c, cudaMemcpyAsync(d.d_baseline, baseline, sizeof(double) * N, cudaMemcpyHostToDevice, d.stream));
+    CU(c, rpf_launch_write_data(d.d_pwr, N, c->repeats_done, tuned_freq, samplerate, linear,
+                                baseline ? d.d_baseline : nullptr, d.d_tmp, d.d_tmp + N, nullptr, d.stream));
+    d.launches++;
+    if (freq_out) CU(c, cudaMemcpyAsync(freq_out, d.d_tmp, sizeof(double) * N, cudaMemcpyDeviceToHost, d.stream));
+    CU(c, cudaMemcpyAsync(val_out, d.d_tmp + N, sizeof(double) * N, cudaMemcpyDeviceToHost, d.stream));
+    return sync_compute_streams(c);
+}
+
+int rpf_write_row_f32(rpf_ctx *c, int32_t samplerate, int32_t linear, const double *baseline, float *row_out)
+{
+    if (!c || !row_out) return RPF_ERR_INVALID_ARG;
+    if (samplerate <= 0) return fail(c, RPF_ERR_INVALID_ARG, "rpf_write_row_f32: samplerate must be > 0");
+    int r = drain_pending(c);
+    if (r) return r;
+    r = reduce_all(c, nullptr);
+    if (r) return r;
+    rpf_dev &d = c->devs[0];
+    CU(c, cudaSetDevice(d.device));
+    const int N = c->N;
+    if (baseline)
+        CU(c, cudaMemcpyAsync(d.d_baseline, baseline, sizeof(double) * N, cudaMemcpyHostToDevice, d.stream));
+    float *d_row = reinterpret_cast<float *>(d.d_tmp);          // N floats at the start of the 2N-double scratch
+    CU(c, rpf_launch_write_data(d.d_pwr, N, c->repeats_done, 0.0, samplerate, linear,
+                                baseline ? d.d_baseline : nullptr, nullptr, d.d_tmp + N, d_row, d.stream));
+    d.launches++;
+    CU(c, cudaMemcpyAsync(row_out, d_row, sizeof(float) * N, cudaMemcpyDeviceToHost, d.stream));
+    return sync_compute_streams(c);
 }
 
 void rpf_synth_fill_host(uint8_t *bytes, size_t len, uint64_t off, uint64_t seed, int32_t mode)
@@ -482,20 +826,36 @@ int rpf_synth_fill_device(uint8_t *bytes, size_t len, uint64_t off, uint64_t see
 {
     if (!bytes && len) return RPF_ERR_INVALID_ARG;
     if (mode < 0 || mode > 2) return RPF_ERR_INVALID_ARG;
-    if (cudaSetDevice(device) != cudaSuccess) return RPF_ERR_CUDA;
-    return rpf_launch_synth(bytes, len, off, seed, mode, (cudaStream_t)cuda_stream) == cudaSuccess ? RPF_OK : RPF_ERR_CUDA;
+    int sms = 0;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+        cudaGetLastError();
+        return RPF_ERR_CUDA;
+    }
+    return rpf_launch_synth(bytes, len, off, seed, mode, sms, (cudaStream_t)cuda_stream) == cudaSuccess ? RPF_OK : RPF_ERR_CUDA;
 }
 
+// A failing runtime call leaves a non-sticky "last error" behind on the calling thread; the launch wrappers
+// return cudaGetLastError() after <<<>>>, so it is cleared here or it would surface at an unrelated launch.
 int rpf_host_alloc(void **out, size_t bytes)
 {
     if (!out) return RPF_ERR_INVALID_ARG;
-    return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? RPF_OK : RPF_ERR_CUDA;
+    if (cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess) return RPF_OK;
+    cudaGetLastError();
+    return RPF_ERR_CUDA;
 }
-void rpf_host_free(void *p) { if (p) cudaFreeHost(p); }
+void rpf_host_free(void *p) { if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError(); }
 int rpf_host_register(void *p, size_t bytes)
 {
-    return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? RPF_OK : RPF_ERR_CUDA;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) return RPF_OK;
+    cudaGetLastError();
+    return RPF_ERR_CUDA;
 }
-int rpf_host_unregister(void *p) { return cudaHostUnregister(p) == cudaSuccess ? RPF_OK : RPF_ERR_CUDA; }
+int rpf_host_unregister(void *p)
+{
+    if (cudaHostUnregister(p) == cudaSuccess) return RPF_OK;
+    cudaGetLastError();
+    return RPF_ERR_CUDA;
+}
 
 }  // extern "C"

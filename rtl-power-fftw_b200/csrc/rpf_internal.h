@@ -26,6 +26,11 @@ cudaError_t rpf_fused3_configure();    // opt-in shared memory attributes (once 
 cudaError_t rpf_launch_pipe4096(const RpfLaunch &L);
 cudaError_t rpf_pipe4096_configure();
 
+// N = 4096 with pass 1 on the tensor cores (tcgen05.mma, fp16 hi+lo DFT-16 matrix; raw bytes, no window): experiment
+// selected with RPF_FLAG_TC_PASS1.
+cudaError_t rpf_launch_pipe4096_tc(const RpfLaunch &L);
+cudaError_t rpf_pipe4096_tc_configure();
+
 // Generic power-of-two N in [2,256]: shared-memory radix-2 Stockham.
 cudaError_t rpf_launch_small(int N, const RpfLaunch &L);
 
@@ -35,16 +40,16 @@ cudaError_t rpf_direct_dft_configure();
 
 // Four-step outer pass for N = M*4096: radix-M over the stride-4096 digit + twiddle.
 cudaError_t rpf_launch_fourstep_outer(int M, const uint8_t *bytes, int64_t nspec, const float2 *twiddle_big,
-                                      const float *window, float2 *scratch, cudaStream_t stream);
+                                      const float *window, float2 *scratch, int sms, cudaStream_t stream);
 
-// pwr[i] = sum over rows (fixed order, float64).
+// pwr[i] = sum over rows [0, nrows) (fixed order, float64).
 cudaError_t rpf_launch_reduce_rows(const double *rows, int nrows, int64_t rowlen, double *pwr, cudaStream_t stream);
 
 cudaError_t rpf_launch_reduce_rows_fourstep(const double *rows, int nrows, int M, int inner, double *pwr, cudaStream_t stream);
 
 cudaError_t rpf_launch_synth(uint8_t *bytes, size_t len, uint64_t stream_offset, uint64_t seed, int mode,
-                             cudaStream_t stream);
+                             int sms, cudaStream_t stream);
 
 cudaError_t rpf_launch_write_data(const double *pwr, int N, int64_t repeats_done, double tuned_freq,
                                   int samplerate, int linear, const double *baseline, double *freq_out,
-                                  double *val_out, cudaStream_t stream);
+                                  double *val_out, float *row_f32_out, cudaStream_t stream);

@@ -75,18 +75,51 @@ void AuxData::load(const Params &params, std::istream &in)
 
 bool SyntheticSource::read(Buffer &buffer)
 {
-    rpf_synth_fill_host(buffer.data(), buffer.size(), offset, seed, mode);
+    const uint64_t sd = per_frequency ? seed ^ ((uint64_t)freq * 0x9E3779B97F4A7C15ull) : seed;
+    rpf_synth_fill_host(buffer.data(), buffer.size(), offset, sd, mode);
     offset += buffer.size();
     return true;
 }
 
 Plan::Plan(Params &p, int rate) : actual_samplerate(rate), params(p)
 {
-    // buffer auto-sizing rule of src/acquisition.cxx:166-176
+    // repeats from the integration time at the TRUE sample rate (src/acquisition.cxx:162-163)
+    if (params.integration_time_isSet)
+        params.repeats = (int64_t)std::ceil(actual_samplerate * params.integration_time / params.N);
+
+    // buffer auto-sizing (src/acquisition.cxx:166-176): up to ~1.6 MB of data -> the smallest multiple of the USB
+    // quantum that holds it, otherwise the default 100 quanta stay
     if (!params.buf_length_isSet) {
         int64_t mult = (int64_t)std::ceil((2.0 * params.N * params.repeats) / base_buf);
         if (mult <= default_buf_multiplier) params.buf_length = base_buf * (mult == 0 ? 1 : mult);
     }
+
+    // centre frequencies (src/acquisition.cxx:180-198): the hops cover [startfreq, stopfreq] with at least
+    // min_overlap percent of the bandwidth shared by neighbours; the surplus is spread evenly as extra overlap
+    if (params.freq_hopping_isSet) {
+        const double span = (double)(params.stopfreq - params.startfreq);
+        const double min_overhang = actual_samplerate * params.min_overlap / 100;
+        const int hops = (int)std::ceil((span - min_overhang) / ((double)actual_samplerate - min_overhang));
+        if (hops > 1) {
+            const int overhang = (int)(((int64_t)hops * actual_samplerate - (params.stopfreq - params.startfreq)) / (hops - 1));
+            freqs_to_tune.push_back((int64_t)(params.startfreq + actual_samplerate / 2.0));
+            for (int hop = 1; hop < hops; hop++) freqs_to_tune.push_back(freqs_to_tune.back() + actual_samplerate - overhang);
+        } else {
+            freqs_to_tune.push_back((params.startfreq + params.stopfreq) / 2);
+        }
+    } else {
+        freqs_to_tune.push_back(params.cfreq);
+    }
+}
+
+void Plan::print(std::ostream &err) const
+{
+    err << "Number of bins: " << params.N << std::endl;
+    err << "Total number of (complex) samples to collect: " << (int64_t)params.N * params.repeats << std::endl;
+    err << "Buffer length: " << params.buf_length << std::endl;
+    err << "Number of averaged spectra: " << params.repeats << std::endl;
+    err << "Estimated time of measurements: " << (double)params.N * params.repeats / actual_samplerate << " seconds"
+        << std::endl;
 }
 
 Acquisition::Acquisition(const Params &p, AuxData &a, SampleSource &s, Datastore &d, int rate, int64_t f)
@@ -146,14 +179,16 @@ void Acquisition::run()
     data.rethrow_worker_error();   // CUDA failure -> RPFexception(HardwareError) on this thread
 }
 
-void Acquisition::print_summary() const
+void Acquisition::print_summary() const { print_summary(std::cerr); }
+
+void Acquisition::print_summary(std::ostream &err) const
 {
-    std::cerr << "Actual number of (complex) samples collected: " << (int64_t)params.N * data.repeats_done << std::endl;
-    std::cerr << "Actual number of device readouts: " << deviceReadouts << std::endl;
-    std::cerr << "Number of successful readouts: " << successfulReadouts << std::endl;
-    std::cerr << "Actual number of averaged spectra: " << data.repeats_done << std::endl;
-    std::cerr << "Effective integration time: " << (double)params.N * data.repeats_done / actual_samplerate
-              << " seconds" << std::endl;
+    err << "Actual number of (complex) samples collected: " << (int64_t)params.N * data.repeats_done << std::endl;
+    err << "Actual number of device readouts: " << deviceReadouts << std::endl;
+    err << "Number of successful readouts: " << successfulReadouts << std::endl;
+    err << "Actual number of averaged spectra: " << data.repeats_done << std::endl;
+    err << "Effective integration time: " << (double)params.N * data.repeats_done / actual_samplerate << " seconds"
+        << std::endl;
 }
 
 // Text output of src/acquisition.cxx:360-433 (non-matrix mode, without the
@@ -162,13 +197,27 @@ void Acquisition::print_summary() const
 void Acquisition::write_data(std::ostream &out) const
 {
     const int N = params.N;
+    if (params.matrixMode) {
+        // one scan row: N float32 values appended to the .bin file (src/acquisition.cxx:385-388,400-405);
+        // normalisation, dB and baseline run on the device, narrowed to float there (fpwrdb = pwrdb, :404)
+        std::vector<float> row(N);
+        int rc = rpf_write_row_f32(data.context(), actual_samplerate, params.linear ? 1 : 0,
+                                   params.baseline ? aux.baseline_values.data() : nullptr, row.data());
+        if (rc != RPF_OK)
+            throw RPFexception(std::string("write_data: ") + rpf_strerror(data.context()), ReturnValue::HardwareError);
+        data.pwr[N / 2] = (data.pwr[N / 2 - 1] + data.pwr[(N / 2 + 1) % N]) / 2;   // :377, as below
+        std::ofstream binfile(params.bin_file, std::ios::out | std::ios::app | std::ios::binary);
+        if (!binfile.good()) throw RPFexception("Could not open " + params.bin_file + ".", ReturnValue::InvalidInput);
+        binfile.write(reinterpret_cast<const char *>(row.data()), (std::streamsize)sizeof(float) * N);
+        return;
+    }
     std::vector<double> f(N), v(N);
     int rc = rpf_write_data(data.context(), (double)tuned_freq, actual_samplerate, params.linear ? 1 : 0,
                             params.baseline ? aux.baseline_values.data() : nullptr, f.data(), v.data());
     if (rc != RPF_OK)
         throw RPFexception(std::string("write_data: ") + rpf_strerror(data.context()), ReturnValue::HardwareError);
     // the reference mutates pwr[N/2] while printing (src/acquisition.cxx:377); keep that visible
-    data.pwr[N / 2] = (data.pwr[N / 2 - 1] + data.pwr[N / 2 + 1]) / 2;
+    data.pwr[N / 2] = (data.pwr[N / 2 - 1] + data.pwr[(N / 2 + 1) % N]) / 2;   // (N = 2: the reference reads past the end)
 
     out << "# rtl-power-fftw output" << std::endl;
     out << "#" << std::endl;

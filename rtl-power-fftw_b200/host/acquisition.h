@@ -3,11 +3,13 @@
 //                   read(Buffer&), set_frequency(), frequency()
 //   SyntheticSource: counter-based IQ bytes (rpf_synth_fill_host) instead of USB
 //   AuxData       : window / baseline values (src/acquisition.h:33-41)
-//   Plan          : repeats / buffer auto-sizing (src/acquisition.cxx:158-176; no hopping)
+//   Plan          : repeats from the integration time, buffer auto-sizing, list of centre frequencies with
+//                   overlap (src/acquisition.cxx:158-208)
 //   Acquisition   : run() / print_summary() / write_data() (src/acquisition.h:81-98)
 #pragma once
 #include <cstdint>
 #include <iosfwd>
+#include <list>
 #include <string>
 #include <vector>
 
@@ -25,13 +27,18 @@ class SampleSource {
 
 class SyntheticSource : public SampleSource {
   public:
-    SyntheticSource(uint64_t seed, int mode) : seed(seed), mode(mode) {}
+    // per_frequency: every centre frequency gets its own byte stream (seed mixed with the frequency), so the hops
+    // of a scan differ; otherwise the same bytes are replayed at every frequency.
+    SyntheticSource(uint64_t seed, int mode, bool per_frequency = false)
+        : seed(seed), mode(mode), per_frequency(per_frequency) {}
     bool read(Buffer &buffer) override;
+    void set_frequency(int64_t f) override { freq = f; offset = 0; }
     void rewind() { offset = 0; }
     uint64_t offset = 0;
   private:
     uint64_t seed;
     int mode;
+    bool per_frequency;
 };
 
 // Window function and baseline read from text (src/acquisition.cxx:32-156): one value per line =
@@ -54,6 +61,8 @@ template <typename T> std::vector<T> read_inputfile(std::istream &stream);
 class Plan {
   public:
     Plan(Params &params, int actual_samplerate);
+    void print(std::ostream &err) const;              // src/acquisition.cxx:200-208
+    std::list<int64_t> freqs_to_tune;                 // src/acquisition.h:53
     int actual_samplerate;
   protected:
     Params &params;
@@ -65,6 +74,9 @@ class Acquisition {
                 int actual_samplerate, int64_t freq);
     void run();
     void print_summary() const;
+    void print_summary(std::ostream &err) const;
+    // Text block on `out`, or -- params.matrixMode -- one float32 row appended to params.bin_file
+    // (src/acquisition.cxx:385-388,400-405).
     void write_data(std::ostream &out) const;
 
     int64_t deviceReadouts = 0, successfulReadouts = 0;

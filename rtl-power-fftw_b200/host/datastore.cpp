@@ -9,6 +9,11 @@ Datastore::Datastore(const Params &p, std::vector<float> &win)
     rpf_config cfg = {};
     cfg.N = params.N;
     cfg.device = params.cuda_device;
+    if (params.cuda_devices.size() > RPF_MAX_DEVICES)
+        throw RPFexception("too many CUDA devices", ReturnValue::InvalidArgument);
+    cfg.n_devices = (int32_t)params.cuda_devices.size();   // 0: the single GPU above
+    for (size_t i = 0; i < params.cuda_devices.size(); i++) cfg.devices[i] = params.cuda_devices[i];
+    if (params.pipelined_push) cfg.flags |= RPF_FLAG_PIPELINED_PUSH;
     cfg.window = params.window ? window_values.data() : nullptr;
     cfg.buf_length = params.buf_length;
     if (params.window && (int)window_values.size() != params.N)
@@ -45,6 +50,14 @@ void Datastore::fftThread()
     int rc = rpf_reset(ctx, params.repeats);
     if (rc != RPF_OK) { worker_status = rc; worker_error = rpf_strerror(ctx); }
 
+    // RPF_FLAG_PIPELINED_PUSH: the copy of buffer k is still in flight when rpf_push returns, so buffer k goes
+    // back to the empty queue only after the push of buffer k+1 (or the final rpf_finish) has returned.
+    Buffer *in_flight = nullptr;
+    auto recycle = [this](Buffer *b) {
+        std::lock_guard<std::mutex> g(status_mutex);
+        empty_buffers.push_back(b);
+        status_change.notify_all();
+    };
     std::unique_lock<std::mutex> lock(status_mutex, std::defer_lock);
     for (;;) {
         lock.lock();
@@ -61,15 +74,23 @@ void Datastore::fftThread()
         }
         // on error: keep returning buffers so Acquisition::run() never blocks forever
 
-        lock.lock();
-        empty_buffers.push_back(buffer);
-        status_change.notify_all();
-        lock.unlock();
+        if (params.pipelined_push && worker_status == 0) {
+            if (in_flight) recycle(in_flight);
+            in_flight = buffer;
+            // with a single buffer in the pool the producer would starve: release it at once (after a sync)
+            if (params.buffers < 2) { rpf_sync(ctx); recycle(in_flight); in_flight = nullptr; }
+        } else {
+            if (in_flight) { rpf_sync(ctx); recycle(in_flight); in_flight = nullptr; }
+            recycle(buffer);
+        }
     }
     if (worker_status == 0) {
         rc = rpf_finish(ctx, pwr.data(), &repeats_done);
         if (rc != RPF_OK) { worker_status = rc; worker_error = rpf_strerror(ctx); }
+    } else {
+        rpf_sync(ctx);
     }
+    if (in_flight) recycle(in_flight);
 }
 
 void Datastore::rethrow_worker_error() const

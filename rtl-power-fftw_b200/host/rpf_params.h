@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 constexpr int base_buf = 16384;              // USB transfer quantum (src/params.h:26)
 constexpr int default_buf_multiplier = 100;  // src/params.h:27
@@ -40,5 +41,15 @@ struct Params {
     std::string baseline_file;                         // "-" = stdin
     bool linear = false;
     bool talkless = true;
+    int64_t startfreq = 0, stopfreq = 0;               // frequency hopping (src/params.h:36-37)
+    bool freq_hopping_isSet = false;
+    double min_overlap = 0;                            // percent (src/params.h:44)
+    double integration_time = 0;                       // seconds (src/params.h:40-41)
+    bool integration_time_isSet = false;
+    bool matrixMode = false;                           // src/params.h:60-66: one float32 row per acquisition -> bin_file
+    std::string bin_file;
+    int64_t finalfreq = 0;
     int cuda_device = 0;                               // new: where the FFT worker runs
+    std::vector<int> cuda_devices;                     // new: several GPUs behind ONE Datastore (rpf_config.devices[])
+    bool pipelined_push = false;                       // new: RPF_FLAG_PIPELINED_PUSH, the worker holds one buffer back
 };

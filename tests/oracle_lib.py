@@ -58,6 +58,10 @@ def oracle():
         lib.rpf_oracle_read_sizes.argtypes = [C.c_int, C.c_int64, C.c_int64, _i64p, C.c_int64]
         lib.rpf_oracle_write_data.argtypes = [C.c_int, _f64p, C.c_int64, C.c_double, C.c_int, C.c_int,
                                               _f64p, _f64p, _f64p]
+        lib.rpf_oracle_plan_repeats.restype = C.c_int64
+        lib.rpf_oracle_plan_repeats.argtypes = [C.c_int, C.c_int, C.c_double]
+        lib.rpf_oracle_plan_freqs.restype = C.c_int
+        lib.rpf_oracle_plan_freqs.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_double, _i64p, C.c_int]
         _oracle = lib
     return _oracle
 
@@ -143,6 +147,13 @@ def oracle_read_sizes(N, repeats, buf_length):
     out = np.zeros(n, dtype=np.int64)
     oracle().rpf_oracle_read_sizes(N, repeats, buf_length, out.ctypes.data_as(_i64p), n)
     return out
+
+
+def oracle_plan_freqs(startfreq, stopfreq, samplerate, min_overlap):
+    n = oracle().rpf_oracle_plan_freqs(startfreq, stopfreq, samplerate, min_overlap, None, 0)
+    out = np.zeros(n, dtype=np.int64)
+    oracle().rpf_oracle_plan_freqs(startfreq, stopfreq, samplerate, min_overlap, out.ctypes.data_as(_i64p), n)
+    return [int(x) for x in out]
 
 
 def oracle_run_stream(N, repeats, stream, window=None, buf_length=None, fft_kind=0, wrap=False):

@@ -29,7 +29,7 @@ def test_header_and_library_agree():
     out = subprocess.run(["nm", "-D", "--defined-only", pkg.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r" T (rpf_[a-z_0-9]+)", out))
     assert set(declared) <= exported
-    assert lib.rpf_abi_version() == 1
+    assert lib.rpf_abi_version() == 2
 
 
 def test_every_entry_point_cites_the_reference():
@@ -167,6 +167,31 @@ def test_auxdata_reader_matches_reference_parser(tmp_path):
         for name, c in cases.items():
             r = subprocess.run([ref, "double"], input=c["text"], capture_output=True, text=True)
             assert r.stdout.split() == c["double"], name
+
+
+def test_plan_matches_oracle():
+    """Plan (host/acquisition.cpp) against the restatement of src/acquisition.cxx:162-198: repeats from the
+    integration time, buffer auto-sizing, the list of centre frequencies with overlap.  No GPU involved."""
+    import oracle_lib as ol
+    exe = os.path.join(ROOT, "rtl-power-fftw_b200", "host", "rpf_power_synth")
+    cases = [(512, 2000000, 0.5, 88000000, 108000000, 0), (512, 2400000, 0.1, 88000000, 108000000, 10),
+             (4096, 2048000, 1.5, 1419000000, 1421000000, 50), (500, 1000000, 0.01, 100000000, 100500000, 0),
+             (1024, 3200000, 2.0, 24000000, 1766000000, 33.3), (512, 2000000, 1e-5, 433000000, 433000001, 0),
+             (2048, 2399999, 0.25, 144000000, 146000000, 99)]
+    for N, rate, t, f0, f1, ov in cases:
+        r = subprocess.run([exe, str(N), "0", "--rate", str(rate), "--integration-time", repr(t), "--freq-range",
+                            "%d:%d" % (f0, f1), "--overlap", repr(ov), "--plan-only"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = dict((ln.split()[0], ln.split()[1:]) for ln in r.stdout.splitlines())
+        rep = ol.oracle().rpf_oracle_plan_repeats(N, rate, t)
+        assert int(out["repeats"][0]) == rep
+        assert int(out["buf_length"][0]) == ol.oracle().rpf_oracle_plan_buf_length(N, rep, 1638400, 0)
+        freqs = ol.oracle_plan_freqs(f0, f1, rate, ov)
+        assert int(out["freqs"][0]) == len(freqs) and [int(x) for x in out["freqs"][1:]] == freqs
+        assert "Number of averaged spectra: %d" % rep in r.stderr
+    # without hopping: the single centre frequency (src/acquisition.cxx:195-197)
+    r = subprocess.run([exe, "512", "100", "--plan-only"], capture_output=True, text=True)
+    assert "freqs 1 1420405752" in r.stdout and "repeats 100" in r.stdout and "buf_length 114688" in r.stdout
 
 
 def test_bench_reference_arm_contract():

@@ -91,3 +91,28 @@ def test_results_are_run_to_run_deterministic():
                 c.push(s[off:off + 1638400])
             outs.append(c.finish()[0])
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_planner_driven_scan_and_matrix_file(tmp_path):
+    """Integration time -> repeats and the hop list (Plan, src/acquisition.cxx:162-198) drive the hop loop; in
+    matrix mode every acquisition appends one float32 row (src/acquisition.cxx:400-405)."""
+    args = ["512", "0", "0", "7", "1", "0", "5", "0", "0", "--rate", "2000000", "--integration-time", "0.01",
+            "--freq-range", "100000000:105000000"]
+    r = subprocess.run([EXE] + args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    rep = ol.oracle().rpf_oracle_plan_repeats(512, 2000000, 0.01)
+    freqs = ol.oracle_plan_freqs(100000000, 105000000, 2000000, 0.0)
+    blocks = [b for b in r.stdout.split("# rtl-power-fftw output") if b.strip()]
+    assert len(blocks) == len(freqs) == 3
+    assert r.stderr.count("Actual number of averaged spectra: %d" % rep) == 3
+    for b, f in zip(blocks, freqs):                                # centre bin of every block = the tuned frequency
+        rows = [ln.split() for ln in b.splitlines() if ln and not ln.startswith("#")]
+        assert len(rows) == 512 and float(rows[256][0]) == pytest.approx(f, abs=1.0)
+    assert blocks[0] != blocks[1]                                  # every hop has its own byte stream
+    m = tmp_path / "scan.bin"
+    r2 = subprocess.run([EXE] + args + ["--matrix", str(m)], capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0 and r2.stdout == ""
+    mat = np.fromfile(m, np.float32).reshape(3, 512)
+    for b, row in zip(blocks, mat):
+        txt = np.array([float(ln.split()[1]) for ln in b.splitlines() if ln and not ln.startswith("#")])
+        assert np.max(np.abs(txt - row)) < 2e-4                    # text has 6 significant digits

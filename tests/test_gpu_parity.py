@@ -324,6 +324,69 @@ def test_window_linearity_config3_shape():
     assert relmax(p50, po) < TOL and np.max(np.abs(p50 - po) / po) < 1e-4
 
 
+@pytest.mark.parametrize("R", [1, 2, 3, 24, 295, 297, 593, 3000])
+def test_tc_pass1_variant_matches_oracle_and_fp32_path(R):
+    """RPF_FLAG_TC_PASS1 (first radix-16 pass on tcgen05 tensor cores, fp16 hi+lo DFT-16 matrix): same gate as the
+    FP32 kernel -- 1e-5 against the float64 oracle -- on every 4096-bin shape the FP32 kernel is tested on."""
+    N = 4096
+    s = stream(2 * N * R, seed=R + 17, mode=R % 3)
+    with Context(N, flags=pkg.capi.RPF_FLAG_TC_PASS1) as c:
+        assert c.plan_name == "pipe4096_tc"
+        c.reset(R)
+        c.push(s)
+        pt, done = c.finish()
+    pf, _ = run_gpu(N, R, [s])
+    assert done == R
+    Ro = min(R, 600)
+    if Ro == R:
+        po, _ = ol.oracle_run_stream(N, R, s, buf_length=s.size)
+        assert relmax(pt, po) < TOL
+        if R >= 24 and R % 3 != 2:
+            assert perbin(pt, po) < TOL
+        assert np.argmax(pt) == np.argmax(po)
+    assert relmax(pt, pf) < 2e-6                           # and against the FP32 kernel on the same bytes
+
+
+def test_tc_pass1_variant_kats_and_stream_semantics():
+    N = 4096
+    F = pkg.capi.RPF_FLAG_TC_PASS1
+    z = np.full(2 * N * 2, 127, np.uint8)
+    with Context(N, flags=F) as c:
+        c.reset(2)
+        c.push(z)
+        p, done = c.finish()
+        assert done == 2 and np.all(p == 0.0)              # exact
+        d = z[: 2 * N].copy()
+        d[0::2] = 127 + 40
+        c.reset(1)
+        c.push(d)
+        p, _ = c.finish()
+        assert np.argmax(p) == N // 2 and p[N // 2] == pytest.approx((40 * N) ** 2, rel=1e-6)
+        assert np.max(np.delete(p, N // 2)) <= 1e-9 * p[N // 2]
+        e = z[: 2 * N].copy()
+        e[0::2] = 0
+        e[1::2] = 255                                      # extreme bytes: -127 / +128 on the two rails
+        c.reset(1)
+        c.push(e)
+        p, _ = c.finish()
+        assert np.argmax(p) == N // 2 and p[N // 2] == pytest.approx(N * N * (127.0 ** 2 + 128.0 ** 2), rel=1e-6)
+        # straddling pushes + Parseval + repeats limit
+        R = 37
+        s = stream(2 * N * R + N, seed=5)
+        c.reset(30)
+        for off in range(0, s.size, 16384 * 5 + 2):
+            c.push(s[off:off + 16384 * 5 + 2])
+        p, done = c.finish()
+        assert done == 30
+        x = s[: 2 * N * 30].astype(np.int64) - 127
+        assert p.sum() == pytest.approx(N * float((x * x).sum()), rel=1e-6)
+        po, _ = ol.oracle_run_stream(N, 30, s, buf_length=s.size)
+        assert perbin(p, po) < TOL
+    w = np.ones(N, np.float32)
+    with Context(N, window=w, flags=F) as c:
+        assert c.plan_name == "fused3"                     # with a window the flag is ignored (FP32 kernel)
+
+
 def test_write_data_matches_oracle():
     import ctypes as C
     N, R = 4096, 9
@@ -344,3 +407,35 @@ def test_write_data_matches_oracle():
             assert np.allclose(v, vo, rtol=1e-13, atol=1e-13)
         pwr2, _ = c.finish()
         assert np.array_equal(pwr, pwr2)               # write_data leaves the accumulator untouched
+
+
+def test_matrix_row_f32_and_smallest_N():
+    """The float32 matrix-mode row (src/acquisition.cxx:400-405: fpwrdb = pwrdb) and write_data at N = 2, where
+    the reference's DC interpolation reads pwr[N/2 + 1] one past the end (the index wraps here)."""
+    import ctypes as C
+    N, R = 1024, 17
+    s = stream(2 * N * R, seed=23)
+    base = np.linspace(0.5, -0.5, N)
+    with Context(N) as c:
+        c.reset(R)
+        c.push(s)
+        pwr, done = c.finish()
+        for linear in (False, True):
+            row = c.write_row_f32(2400000, linear=linear, baseline=base)
+            _, v = c.write_data(0.0, 2400000, linear=linear, baseline=base)
+            fo, vo = np.zeros(N), np.zeros(N)
+            p = pwr.copy()
+            dp = C.POINTER(C.c_double)
+            ol.oracle().rpf_oracle_write_data(N, p.ctypes.data_as(dp), done, 0.0, 2400000, int(linear),
+                                              base.ctypes.data_as(dp), fo.ctypes.data_as(dp), vo.ctypes.data_as(dp))
+            assert row.dtype == np.float32 and np.array_equal(row, v.astype(np.float32))
+            assert np.allclose(row, vo.astype(np.float32), rtol=2e-6, atol=2e-6)
+    with Context(2) as c:
+        t = np.array([130, 120, 100, 140] * 5, np.uint8)
+        c.reset(10)
+        c.push(t)
+        p2, d2 = c.finish()
+        f, v = c.write_data(1.0e6, 1000, linear=True)
+        assert d2 == 10 and np.all(np.isfinite(v))
+        assert v[1] == pytest.approx(p2[0] / d2 / 2 / 1000, rel=1e-12)       # mean of the two neighbours = pwr[0]
+        assert v[0] == pytest.approx(p2[0] / d2 / 2 / 1000, rel=1e-12)
