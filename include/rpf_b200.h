@@ -48,8 +48,9 @@ extern "C" {
 typedef enum rpf_status {
     RPF_OK = 0,
     RPF_ERR_INVALID_ARG = -1,   /* NULL pointer, odd byte count, N odd or < 2 ...            */
-    RPF_ERR_UNSUPPORTED_N = -2, /* N is valid for the reference but not implemented on GPU:
-                                   supported are powers of two 2..65536 and any even N <= 8190 */
+    RPF_ERR_UNSUPPORTED_N = -2, /* N is valid for the reference but not implemented on GPU: every even N
+                                   from 2 to 4194304 is supported (fused kernels for powers of two up to
+                                   65536, Bluestein / plain O(N log N) FFT passes for the rest)          */
     RPF_ERR_CUDA = -3,          /* a CUDA runtime call or kernel failed (message has detail) */
     RPF_ERR_NOMEM = -4,
     RPF_ERR_STATE = -5          /* call sequence error                                       */
@@ -159,7 +160,8 @@ int32_t rpf_device_count(const rpf_ctx *ctx);
 /* Number of this library's kernel launches issued by the context so far. */
 int64_t rpf_kernel_launches(const rpf_ctx *ctx);
 
-/* Name of the kernel family selected for this N ("small", "fused3", "fourstep", "direct"). */
+/* Name of the kernel family selected for this N ("small", "fused3", "pipe4096_tc", "fourstep", "direct",
+ * "bluestein", "gfft"). */
 const char *rpf_plan_name(const rpf_ctx *ctx);
 
 /* ---- Acquisition::write_data() arithmetic on the device ------------------

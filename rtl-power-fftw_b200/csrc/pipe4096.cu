@@ -187,11 +187,16 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
             }
             for (int j = 0; j < nit; j++) {
                 const uint32_t ph = (uint32_t)(j & 1);
+#ifdef RPF_COPYLANE_HINT_NS
+#define RPF_LANE_WAIT(bar, par) mbar_wait_parked((bar), (par), RPF_COPYLANE_HINT_NS)
+#else
+#define RPF_LANE_WAIT(bar, par) mbar_wait((bar), (par))
+#endif
                 mbar_arrive(sm + 8 * bar_rd(0, 1));
-                mbar_wait(sm + 8 * bar_rd(0, 1), ph);                  // every compute warp has stored its (A,1) rows
+                RPF_LANE_WAIT(sm + 8 * bar_rd(0, 1), ph);              // every compute warp has stored its (A,1) rows
                 if (j + kStg <= nit) issue(0, j + kStg);               // ... so A's ring slot is free
                 mbar_arrive(sm + 8 * bar_rd(1, 1));
-                mbar_wait(sm + 8 * bar_rd(1, 1), ph);
+                RPF_LANE_WAIT(sm + 8 * bar_rd(1, 1), ph);
                 if (j + kStg < nit) issue(1, j + kStg);
             }
         }

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -26,7 +27,10 @@ constexpr int kInnerN = 4096;              // inner transform length of the four
 constexpr size_t kSmallPush = 256 << 10;   // pushes up to this size go through a pinned bounce buffer (no host wait)
 constexpr size_t kMinPartBytes = 1 << 20;  // a push is split over the devices only in parts of at least this size
 
-enum PlanKind { PLAN_SMALL, PLAN_FUSED3, PLAN_FOURSTEP, PLAN_DIRECT };
+enum PlanKind { PLAN_SMALL, PLAN_FUSED3, PLAN_FOURSTEP, PLAN_DIRECT, PLAN_BLUESTEIN };
+constexpr int kMaxBins = 1 << 22;          // largest N accepted (pwr[] of 32 MiB; the reference has no limit but memory)
+constexpr int kDirectMaxN = 128;           // non-power-of-two N up to here: O(N^2) kernel; above: Bluestein
+constexpr int kBlueSlices = 64;            // private accumulator rows of the Bluestein path (at most)
 
 thread_local char g_create_err[256] = "";
 
@@ -88,6 +92,7 @@ struct rpf_dev {
     float *d_window = nullptr;
     double *d_rows = nullptr, *d_pwr = nullptr, *d_tmp = nullptr, *d_baseline = nullptr;
     float2 *d_scratch = nullptr;
+    float2 *d_chirp = nullptr, *d_bhat = nullptr, *d_blue[2] = {};   // Bluestein tables and ping-pong buffers
     ncclComm_t comm = nullptr;
     int64_t launches = 0;
 };
@@ -106,12 +111,15 @@ struct rpf_ctx {
     bool use_tc = false;              // RPF_FLAG_TC_PASS1 and N=4096 without window: pipe4096_tc_kernel
     bool pipelined = false;           // RPF_FLAG_PIPELINED_PUSH
     int64_t scratch_spectra = 0;
+    int blueM = 0;                    // PLAN_BLUESTEIN: transform length M (= N for a plain power-of-two FFT)
+    int64_t blue_batch = 0;           // spectra per pass over the ping-pong buffers
 
     std::vector<rpf_dev> devs;        // devs[0] is the primary: results are read from it
     int cursor = 0;                   // next device of the round-robin
     int comm_rank = 0, comm_nranks = 1;   // multi-process communicator (rpf_comm_init_rank); 1 = none
 
     uint8_t *h_carry[kNumStage] = {};   // pinned; the partial spectrum kept for the next push
+    double *h_pwr = nullptr;          // pinned + device-visible: single-GPU rpf_finish reduces straight into it
     int cslot = 0;
     size_t carry_bytes = 0;
     struct Pending { int dev, slot; };
@@ -163,6 +171,31 @@ void fill_twiddle(std::vector<float2> &t, int n)
     }
 }
 
+// float64 radix-2 FFT (forward) for the Bluestein filter table; n = re.size() is a power of two
+void host_fft_pow2(std::vector<double> &re, std::vector<double> &im)
+{
+    const size_t n = re.size();
+    const double PI = 3.14159265358979323846264338327950288;
+    for (size_t i = 1, j = 0; i < n; i++) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const size_t half = len >> 1;
+        for (size_t k = 0; k < half; k++) {
+            const double a = -2.0 * PI * (double)k / (double)len, wr = cos(a), wi = sin(a);
+            for (size_t base = 0; base < n; base += len) {
+                const size_t p = base + k, q = p + half;
+                const double tr = re[q] * wr - im[q] * wi, ti = re[q] * wi + im[q] * wr;
+                re[q] = re[p] - tr; im[q] = im[p] - ti;
+                re[p] += tr; im[p] += ti;
+            }
+        }
+    }
+}
+
 int ensure_stage(rpf_ctx *c, rpf_dev &d, size_t need)
 {
     if (need <= d.stage_cap) return RPF_OK;
@@ -188,6 +221,7 @@ int rows_touched(const rpf_ctx *c, const rpf_dev &d, int64_t nspec)
             blocks = c->usepipe ? (nspec + 1) / 2 : (nspec + c->groups - 1) / c->groups;
             break;
         case PLAN_FOURSTEP: return d.nrows;
+        case PLAN_BLUESTEIN: return d.nrows;
         default: blocks = nspec;
     }
     if (blocks > d.grid) blocks = d.grid;
@@ -212,6 +246,17 @@ int launch_spectra(rpf_ctx *c, rpf_dev &d, const uint8_t *src, int64_t nspec)
     } else if (c->plan == PLAN_DIRECT) {
         CU(c, rpf_launch_direct_dft(c->N, L));
         d.launches++;
+    } else if (c->plan == PLAN_BLUESTEIN) {
+        RpfBluestein B;
+        B.N = c->N; B.M = c->blueM; B.chirp = d.d_chirp; B.bhat = d.d_bhat; B.twM = d.d_twiddle; B.window = d.d_window;
+        B.buf0 = d.d_blue[0]; B.buf1 = d.d_blue[1]; B.rows = d.d_rows; B.slices = d.grid; B.sms = d.sms;
+        B.stream = d.stream;
+        for (int64_t done = 0; done < nspec; done += c->blue_batch) {
+            const int64_t b = (nspec - done) < c->blue_batch ? (nspec - done) : c->blue_batch;
+            int n = 0;
+            CU(c, rpf_launch_bluestein(B, src + (size_t)done * c->spectrum_bytes, b, &n));
+            d.launches += n;
+        }
     } else {
         for (int64_t done = 0; done < nspec; done += c->scratch_spectra) {
             const int64_t b = (nspec - done) < c->scratch_spectra ? (nspec - done) : c->scratch_spectra;
@@ -265,6 +310,36 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
         case PLAN_SMALL:
             d.grid = 8 * sms;
             break;
+        case PLAN_BLUESTEIN: {
+            // tables in double on the host: chirp c[n] = exp(-i pi (n^2 mod 2N) / N) and Bhat = FFT_M(b) / M with
+            // b[n] = b[M - n] = conj c[n] for n < N, zero elsewhere
+            const int M = c->blueM;
+            inner = M;
+            // private rows: up to 64 slices of the batch, but no more than 64 MiB of accumulators
+            int64_t slices = ((int64_t)64 << 20) / ((int64_t)N * (int64_t)sizeof(double));
+            d.grid = (int)(slices < 2 ? 2 : slices > kBlueSlices ? kBlueSlices : slices);
+            CU(c, cudaMalloc(&d.d_blue[0], (size_t)c->blue_batch * M * sizeof(float2)));
+            CU(c, cudaMalloc(&d.d_blue[1], (size_t)c->blue_batch * M * sizeof(float2)));
+            if (M != N) {
+                std::vector<float2> ch(N), bh(M);
+                std::vector<double> br(M, 0.0), bi(M, 0.0);
+                const double PI = 3.14159265358979323846264338327950288;
+                for (int n = 0; n < N; n++) {
+                    const int64_t ph = ((int64_t)n * n) % (2 * (int64_t)N);
+                    const double a = PI * (double)ph / (double)N;
+                    ch[n] = make_float2((float)cos(a), (float)(-sin(a)));
+                    br[n] = cos(a); bi[n] = sin(a);
+                    if (n) { br[M - n] = cos(a); bi[M - n] = sin(a); }
+                }
+                host_fft_pow2(br, bi);                           // float64, in place
+                for (int k = 0; k < M; k++) bh[k] = make_float2((float)(br[k] / M), (float)(bi[k] / M));
+                CU(c, cudaMalloc(&d.d_chirp, sizeof(float2) * N));
+                CU(c, cudaMemcpy(d.d_chirp, ch.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+                CU(c, cudaMalloc(&d.d_bhat, sizeof(float2) * M));
+                CU(c, cudaMemcpy(d.d_bhat, bh.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+            }
+            break;
+        }
         case PLAN_FOURSTEP: {
             // inner transform = pipe4096 in complex-source mode: every CTA is bound to one outer bin, so the
             // grid is a multiple of M (CTAs are persistent; co-residency is not required for correctness)
@@ -378,9 +453,8 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
     const int N = cfg->N;
     if (N < 2 || (N & 1))
         return fail(nullptr, RPF_ERR_INVALID_ARG, "rpf_create: N=%d must be even and >= 2 (src/params.cxx:152-155)", N);
-    if ((!is_pow2(N) && N > 8190) || N > 16 * kInnerN)
-        return fail(nullptr, RPF_ERR_UNSUPPORTED_N,
-                    "rpf_create: N=%d not supported by the CUDA path (powers of two up to 65536, other even N up to 8190)", N);
+    if (N > kMaxBins)
+        return fail(nullptr, RPF_ERR_UNSUPPORTED_N, "rpf_create: N=%d not supported by the CUDA path (even N up to %d)", N, kMaxBins);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -406,8 +480,13 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
     c->has_window = cfg->window != nullptr;
     c->pipelined = (cfg->flags & RPF_FLAG_PIPELINED_PUSH) != 0;
     auto body = [&]() -> int {
-        if (!is_pow2(N)) {
+        if (!is_pow2(N) && N <= kDirectMaxN) {
             c->plan = PLAN_DIRECT; c->groups = 1;
+        } else if (!is_pow2(N) || N > 16 * kInnerN) {
+            c->plan = PLAN_BLUESTEIN; c->groups = 1;
+            c->blueM = rpf_bluestein_M(N);
+            c->blue_batch = ((size_t)128 << 20) / ((size_t)c->blueM * sizeof(float2));   // 2 x 128 MiB ping-pong
+            if (c->blue_batch < 1) c->blue_batch = 1;
         } else if (rpf_fused3_supported(N)) {
             c->plan = PLAN_FUSED3;
             c->usepipe = (N == kInnerN);
@@ -431,6 +510,7 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
         }
         for (int i = 0; i < kNumStage; i++)
             CU(c, cudaHostAlloc((void **)&c->h_carry[i], c->spectrum_bytes, cudaHostAllocDefault));
+        CU(c, cudaHostAlloc((void **)&c->h_pwr, sizeof(double) * N, cudaHostAllocMapped));
         if (nd > 1) {
             // single process, ncclCommInitAll over the context's devices
             NcclApi *api = nccl_api();
@@ -470,11 +550,13 @@ void rpf_destroy(rpf_ctx *c)
         }
         cudaFree(d.d_twiddle); cudaFree(d.d_twiddle_big); cudaFree(d.d_window);
         cudaFree(d.d_rows); cudaFree(d.d_pwr); cudaFree(d.d_tmp); cudaFree(d.d_baseline); cudaFree(d.d_scratch);
+        cudaFree(d.d_chirp); cudaFree(d.d_bhat); cudaFree(d.d_blue[0]); cudaFree(d.d_blue[1]);
         if (d.own_stream) cudaStreamDestroy(d.own_stream);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     }
     for (int i = 0; i < kNumStage; i++)
         if (c->h_carry[i]) cudaFreeHost(c->h_carry[i]);
+    if (c->h_pwr) cudaFreeHost(c->h_pwr);
     cudaGetLastError();
     delete c;
 }
@@ -547,11 +629,12 @@ int rpf_push(rpf_ctx *c, const uint8_t *bytes, size_t len)
         if (part_bytes <= kSmallPush + sb && !c->pipelined) {
             // short read (config 1: one 114,688-byte buffer): bounce through pinned memory on the compute stream;
             // the caller's buffer is free as soon as the host memcpy returns, nobody waits for an event
+            // (the kernels read the pinned bounce buffer in place -- TMA over PCIe -- so there is no separate copy
+            // operation either: for ~100 KB the launch gaps of a memcpy cost more than the transfer)
             CU(c, cudaEventSynchronize(d.ev_consumed[s]));       // bounce slot free (3 pushes ago)
             if (from_carry) memcpy(d.h_bounce[s], c->h_carry[cs], from_carry);
             memcpy(d.h_bounce[s] + from_carry, src, from_new);
-            CU(c, cudaMemcpyAsync(d.d_stage[s], d.h_bounce[s], part_bytes, cudaMemcpyHostToDevice, d.stream));
-            r = launch_spectra(c, d, d.d_stage[s], s1 - s0);
+            r = launch_spectra(c, d, d.h_bounce[s], s1 - s0);
             if (r) return r;
             CU(c, cudaEventRecord(d.ev_consumed[s], d.stream));
         } else {
@@ -693,7 +776,13 @@ int rpf_finish(rpf_ctx *c, double *pwr_out, int64_t *repeats_done)
     int r = drain_pending(c);
     if (r) return r;
     rpf_dev &d0 = c->devs[0];
-    if (pwr_out) {
+    const bool direct = pwr_out && c->devs.size() == 1 && c->comm_nranks == 1;
+    if (direct) {
+        // one GPU: the reduction writes pwr[] straight into device-visible pinned host memory (no D2H operation)
+        CU(c, cudaSetDevice(d0.device));
+        r = reduce_device(c, d0, c->h_pwr);
+        if (r) return r;
+    } else if (pwr_out) {
         r = reduce_all(c, nullptr);
         if (r) return r;
         CU(c, cudaSetDevice(d0.device));
@@ -701,6 +790,7 @@ int rpf_finish(rpf_ctx *c, double *pwr_out, int64_t *repeats_done)
     }
     r = sync_compute_streams(c);
     if (r) return r;
+    if (direct) memcpy(pwr_out, c->h_pwr, sizeof(double) * c->N);
     if (repeats_done) *repeats_done = c->repeats_done;
     return RPF_OK;
 }
@@ -719,6 +809,7 @@ const char *rpf_plan_name(const rpf_ctx *c)
 {
     if (!c) return "";
     if (c->use_tc) return "pipe4096_tc";
+    if (c->plan == PLAN_BLUESTEIN) return c->blueM == c->N ? "gfft" : "bluestein";
     return c->plan == PLAN_SMALL ? "small" : c->plan == PLAN_FUSED3 ? "fused3" : c->plan == PLAN_DIRECT ? "direct" : "fourstep";
 }
 

@@ -38,6 +38,23 @@ cudaError_t rpf_launch_small(int N, const RpfLaunch &L);
 cudaError_t rpf_launch_direct_dft(int N, const RpfLaunch &L);
 cudaError_t rpf_direct_dft_configure();
 
+// Any other even N in O(N log N): Bluestein over M = 2^m >= 2N - 1 (N not a power of two) or a plain FFT_N
+// (N = 2^m > 65536), batched global-memory Stockham passes.  Buffers and tables are owned by the caller.
+struct RpfBluestein {
+    int N, M;                 // M = rpf_bluestein_M(N)
+    const float2 *chirp;      // c[n] = exp(-i pi n^2 / N), n < N            (unused when M == N)
+    const float2 *bhat;       // FFT_M(conj c, wrapped) / M                  (unused when M == N)
+    const float2 *twM;        // W_M^j, j < M
+    const float  *window;     // N floats or nullptr
+    float2 *buf0, *buf1;      // 2 x batch x M complex64
+    double *rows;             // [slices][N] private accumulator rows
+    int slices;
+    int sms;
+    cudaStream_t stream;
+};
+int rpf_bluestein_M(int N);
+cudaError_t rpf_launch_bluestein(const RpfBluestein &B, const uint8_t *bytes, int64_t nspec, int *launches);
+
 // Four-step outer pass for N = M*4096: radix-M over the stride-4096 digit + twiddle.
 cudaError_t rpf_launch_fourstep_outer(int M, const uint8_t *bytes, int64_t nspec, const float2 *twiddle_big,
                                       const float *window, float2 *scratch, int sms, cudaStream_t stream);

@@ -35,6 +35,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     } while (!done);
 }
 
+// Same wait for a thread with nothing else to do (the bulk-copy lane): the try_wait carries a suspend-time hint, so
+// the warp is parked by the hardware instead of re-issuing the probe back to back.
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, uint32_t hint_ns)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+    } while (!done);
+}
+
 // u8 pair (I | Q<<8) -> complex float carrying a +32768 offset on both rails:
 // PRMT builds 0x4700XX00 = 32768.0f + XX exactly (byte into mantissa bits 15:8).
 // No window: the offset (32768+127 per rail) is left in; every butterfly sum of

@@ -48,8 +48,12 @@ void AuxData::load(const Params &params, std::istream &in)
         for (int i = params.N; i < 2 * params.N; i++) baseline_values.push_back(values[i]);
         return;
     }
+    // ONE ifstream serves both files, as in the reference (src/acquisition.cxx:62,108,132): after the window file
+    // has been read to its end, open() on the still-open stream fails, so "window from a file AND baseline from a
+    // file" ends in "Could not open <baseline_file>" there -- at most one of the two can come from a file, the
+    // other from stdin.  Kept as is (same error text and exit code); see DESIGN.md section 8.
+    std::ifstream fs;
     auto open_and_read = [&](const std::string &file, bool as_float) {
-        std::ifstream fs;
         std::istream *stream = &in;
         if (file != "-") {
             fs.open(file);
@@ -223,8 +227,13 @@ void Acquisition::write_data(std::ostream &out) const
     out << "#" << std::endl;
     out << "# frequency [Hz] power spectral density [dB/Hz]" << std::endl;
     const int extraDigitsFreq = 2;
-    const int significantPlacesFreq =
-        (int)std::ceil(std::floor(std::log10((double)tuned_freq)) - std::log10((double)actual_samplerate / N) + 1 + extraDigitsFreq);
+    // src/acquisition.cxx:381-382: actual_samplerate / params.N is an INTEGER division there (bin width truncated to
+    // whole Hz); with N > samplerate it is 0 and the expression overflows to a negative precision, which iostreams
+    // treat as the default 6
+    const int binHz = actual_samplerate / N;
+    const int significantPlacesFreq = binHz > 0
+        ? (int)std::ceil(std::floor(std::log10((double)tuned_freq)) - std::log10((double)binHz) + 1 + extraDigitsFreq)
+        : 6;
     const int significantPlacesPwr = 6;
     for (int i = 0; i < N; i++)
         out << std::setprecision(significantPlacesFreq) << f[i] << " " << std::setprecision(significantPlacesPwr)

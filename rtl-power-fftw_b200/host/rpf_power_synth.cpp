@@ -84,6 +84,8 @@ int main(int argc, char **argv)
             else if (a == "--hop-parallel") hop_parallel = true;
             else throw RPFexception("unknown option " + a, ReturnValue::InvalidArgument);
         }
+        // stdout is the data channel (gnuplot text / nothing in matrix mode): keep NCCL's own log lines off it
+        if (params.cuda_devices.size() > 1) setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
         if (params.buf_length % base_buf != 0)                     // src/params.cxx:166-170
             params.buf_length = (int)(std::floor((double)params.buf_length / base_buf + 0.5) * base_buf);
 

@@ -70,8 +70,8 @@ def test_create_argument_validation_without_gpu():
     cfg.N = 511
     assert lib.rpf_create(C.byref(cfg), C.byref(h)) == -1
     assert b"even" in lib.rpf_strerror(None)
-    cfg.N = 10000
-    assert lib.rpf_create(C.byref(cfg), C.byref(h)) == -2      # valid for the reference; loud, not silent
+    cfg.N = (1 << 22) + 2
+    assert lib.rpf_create(C.byref(cfg), C.byref(h)) == -2      # valid for the reference, beyond the CUDA path: loud
     assert b"not supported" in lib.rpf_strerror(None)
     lib.rpf_destroy(None)                                       # NULL allowed
 
@@ -109,7 +109,9 @@ def test_auxdata_text_reader(tmp_path):
     b = tmp_path / "base.txt"
     b.write_text("".join("%d %.17g\n" % (i, -1.5 + i * 0.1234567890123) for i in range(N)))
     args = [exe, str(N), "1", "0", "1", "1", "0", "5", "0", "0"]
-    r = subprocess.run(args + ["-w", str(w), "-B", str(b), "--dump-aux"], capture_output=True, text=True)
+    # window from a file, baseline from stdin (with both from FILES the reference fails to open the second one: it
+    # re-opens one std::ifstream, src/acquisition.cxx:62,108,132 -- reproduced below)
+    r = subprocess.run(args + ["-w", str(w), "-B", "-", "--dump-aux"], input=b.read_text(), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     lines = r.stdout.split()
     assert lines[0] == "window" and int(lines[1]) == N
@@ -118,6 +120,8 @@ def test_auxdata_text_reader(tmp_path):
     assert lines[2 + N] == "baseline" and int(lines[3 + N]) == N
     base = np.array(lines[4 + N:4 + 2 * N], dtype=np.float64)
     assert np.array_equal(base, np.array([-1.5 + i * 0.1234567890123 for i in range(N)]))
+    r = subprocess.run(args + ["-w", str(w), "-B", str(b), "--dump-aux"], capture_output=True, text=True)
+    assert r.returncode == 5 and "Could not open %s. Quitting." % b in r.stderr
     # both from stdin: first N -> window, next N -> baseline
     both = "".join("%g\n" % v for v in list(range(N)) + [10 + v for v in range(N)])
     r = subprocess.run(args + ["-w", "-", "-B", "-", "--dump-aux"], input=both, capture_output=True, text=True)
@@ -189,6 +193,15 @@ def test_plan_matches_oracle():
         freqs = ol.oracle_plan_freqs(f0, f1, rate, ov)
         assert int(out["freqs"][0]) == len(freqs) and [int(x) for x in out["freqs"][1:]] == freqs
         assert "Number of averaged spectra: %d" % rep in r.stderr
+        # ... and against the reference's OWN Plan::Plan (src/acquisition.cxx:158-198 compiled unmodified into
+        # oracle/_ref/ref_rtl_power), where the reference sources are present
+        ref_bin = os.path.join(ROOT, "oracle", "_ref", "ref_rtl_power")
+        if os.path.exists(ref_bin):
+            rr = subprocess.run([ref_bin, "/dev/null", str(N), "0", "--rate", str(rate), "--integration-time", repr(t),
+                                 "--freq-range", "%d:%d" % (f0, f1), "--overlap", repr(ov), "--plan-only"],
+                                capture_output=True, text=True)
+            assert rr.returncode == 0, rr.stderr
+            assert rr.stdout == r.stdout, (rr.stdout, r.stdout)
     # without hopping: the single centre frequency (src/acquisition.cxx:195-197)
     r = subprocess.run([exe, "512", "100", "--plan-only"], capture_output=True, text=True)
     assert "freqs 1 1420405752" in r.stdout and "repeats 100" in r.stdout and "buf_length 114688" in r.stdout

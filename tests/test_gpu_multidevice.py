@@ -118,6 +118,7 @@ def test_spanning_context_pipelined_push_and_device_buffers():
             c.push_device(t.data_ptr(), t.numel())
         pd, dd = c.finish()
         assert dd == R and perbin(pd, p) < 2e-6
+        c.reset(R)
         with pytest.raises(RpfError):
             c.push_device(bufs[0].data_ptr(), 2 * N + 2)    # a partial spectrum cannot be carried across GPUs
     with Context(N) as c1:

@@ -20,10 +20,13 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--window", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--lib", default=None, help="alternative librpf_b200.so (A/B builds under variants/)")
     ap.add_argument("--flags", type=int, default=0, help="rpf_config.flags (1 = RPF_FLAG_TC_PASS1)")
     a = ap.parse_args()
     import torch
     pkg = importlib.import_module("rtl-power-fftw_b200")
+    if a.lib:
+        pkg.capi.LIB_PATH = os.path.abspath(a.lib)       # before the first lib() call
     import oracle_lib as ol
     peak = 6553.9
     for N in a.n:
