@@ -376,6 +376,38 @@ def bench_config1(pkg, local, reps=300):
             "launches_total": int(launches)}
 
 
+def check_parity(pkg, torch, dist, stream_dev, pwr_dev, pw, nspec, nbytes, cur, dev, local, rank, world, allsum):
+    """Exact Parseval of the timed result over every rank's stream, allreduce == sum of the gathered per-rank
+    vectors (rank order, float64), rank 0's 64-spectrum prefix against the float64 oracle."""
+    rhs = allsum(parseval_rhs(torch, stream_dev, N_BINS))            # N * sum |x - 127|^2 over every rank's stream
+    parity = {"parseval_rel": abs(pw.sum() - rhs) / rhs}
+    with pkg.Context(N_BINS, device=local) as cl:                    # no communicator: this rank's own vector
+        cl.set_stream(cur.cuda_stream)
+        cl.reset(nspec)
+        cl.push_device(stream_dev.data_ptr(), nbytes)
+        local_dev = torch.zeros(N_BINS, dtype=torch.float64, device=dev)
+        cl.finish_device(local_dev.data_ptr())
+        torch.cuda.synchronize()
+    if world > 1:
+        gathered = [torch.zeros_like(local_dev) for _ in range(world)]
+        dist.all_gather(gathered, local_dev)
+        ssum = torch.zeros_like(local_dev)
+        for g in gathered:                                           # rank order, float64
+            ssum += g
+        parity["allreduce_vs_gathered_sum_rel"] = float(((pwr_dev - ssum).abs() / ssum).max().item())
+    else:
+        parity["allreduce_vs_gathered_sum_rel"] = float(((pwr_dev - local_dev).abs() / local_dev).max().item())
+    if rank == 0:
+        perbin, relmax = oracle_prefix_err(pkg, torch, stream_dev, N_BINS, 64, None, local)
+        parity["oracle_prefix_perbin_rank0"] = perbin
+    parity["ok"] = bool(np.all(np.isfinite(pw)) and parity["parseval_rel"] < 1e-6 and
+                        parity["allreduce_vs_gathered_sum_rel"] < 1e-12 and
+                        parity.get("oracle_prefix_perbin_rank0", 0.0) < 1e-5)
+    assert parity["ok"], parity
+
+    return parity
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -386,6 +418,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[] legs (1, 3, 4 / 5)")
+    ap.add_argument("--no-parity", action="store_true", help=argparse.SUPPRESS)   # ncu launch lists: only the step's kernels
     ap.add_argument("--flags", type=int, default=0, help=argparse.SUPPRESS)   # rpf_config.flags of the timed context
     args = ap.parse_args()
     if args.impl == "reference":
@@ -481,32 +514,9 @@ def main():
 
     # ---- parity of the timed result (no skipped work, nothing lost in the reduction) ----------
     pw = pwr_dev.cpu().numpy()
-    rhs = allsum(parseval_rhs(torch, stream_dev, N_BINS))            # N * sum |x - 127|^2 over every rank's stream
-    parity = {"parseval_rel": abs(pw.sum() - rhs) / rhs}
-    with pkg.Context(N_BINS, device=local) as cl:                    # no communicator: this rank's own vector
-        cl.set_stream(cur.cuda_stream)
-        cl.reset(nspec)
-        cl.push_device(stream_dev.data_ptr(), nbytes)
-        local_dev = torch.zeros(N_BINS, dtype=torch.float64, device=dev)
-        cl.finish_device(local_dev.data_ptr())
-        torch.cuda.synchronize()
-    if world > 1:
-        gathered = [torch.zeros_like(local_dev) for _ in range(world)]
-        dist.all_gather(gathered, local_dev)
-        ssum = torch.zeros_like(local_dev)
-        for g in gathered:                                           # rank order, float64
-            ssum += g
-        parity["allreduce_vs_gathered_sum_rel"] = float(((pwr_dev - ssum).abs() / ssum).max().item())
-    else:
-        parity["allreduce_vs_gathered_sum_rel"] = float(((pwr_dev - local_dev).abs() / local_dev).max().item())
-    if rank == 0:
-        perbin, relmax = oracle_prefix_err(pkg, torch, stream_dev, N_BINS, 64, None, local)
-        parity["oracle_prefix_perbin_rank0"] = perbin
-    parity["ok"] = bool(np.all(np.isfinite(pw)) and parity["parseval_rel"] < 1e-6 and
-                        parity["allreduce_vs_gathered_sum_rel"] < 1e-12 and
-                        parity.get("oracle_prefix_perbin_rank0", 0.0) < 1e-5)
-    assert parity["ok"], parity
-
+    parity = None
+    if not args.no_parity:
+        parity = check_parity(pkg, torch, dist, stream_dev, pwr_dev, pw, nspec, nbytes, cur, dev, local, rank, world, allsum)
     # ---- e2e: host buffers through the C ABI, full integration per step ----------------------
     e2e = None
     if not args.no_e2e:

@@ -83,6 +83,12 @@ typedef struct rpf_config {
  * until the next rpf_push / rpf_sync / rpf_finish on this context returns (so two buffers are in flight
  * and the PCIe link never idles between buffers).  Without the flag `bytes` is free on return. */
 #define RPF_FLAG_PIPELINED_PUSH 2u
+/* A/B comparisons only (N = 512, 1024, 2048): run the round-1 lock-step kernel (two CTAs per SM, __syncthreads
+ * between the passes) instead of the two-stream pipeline. */
+#define RPF_FLAG_LOCKSTEP 4u
+/* A/B comparisons only: force the two-stream pipeline where the lock-step kernel is the default (N = 512 without a
+ * window). */
+#define RPF_FLAG_PIPELINE 8u
 
 /* Plays the role of fftwf_alloc_complex x2 + fftwf_plan_dft_1d(N, in, out,
  * FFTW_FORWARD, FFTW_MEASURE) in Datastore::Datastore (src/datastore.cxx:30-33):

@@ -8,6 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librpf_b200.so")
 RPF_FLAG_TC_PASS1 = 1
 RPF_FLAG_PIPELINED_PUSH = 2
+RPF_FLAG_LOCKSTEP = 4
+RPF_FLAG_PIPELINE = 8
 RPF_MAX_DEVICES = 16
 
 EXPORTED_SYMBOLS = [

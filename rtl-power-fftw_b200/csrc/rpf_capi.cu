@@ -109,6 +109,7 @@ struct rpf_ctx {
     bool has_window = false;
     bool usepipe = false;             // N=4096 (and the four-step inner transform): pipe4096_kernel
     bool use_tc = false;              // RPF_FLAG_TC_PASS1 and N=4096 without window: pipe4096_tc_kernel
+    bool use_pipen = false;           // N = 512, 1024, 2048: pipen_kernel (unless RPF_FLAG_LOCKSTEP)
     bool pipelined = false;           // RPF_FLAG_PIPELINED_PUSH
     int64_t scratch_spectra = 0;
     int blueM = 0;                    // PLAN_BLUESTEIN: transform length M (= N for a plain power-of-two FFT)
@@ -219,6 +220,7 @@ int rows_touched(const rpf_ctx *c, const rpf_dev &d, int64_t nspec)
     switch (c->plan) {
         case PLAN_FUSED3:
             blocks = c->usepipe ? (nspec + 1) / 2 : (nspec + c->groups - 1) / c->groups;
+            if (c->use_pipen) blocks = (blocks + 1) / 2;               // pairs of group iterations
             break;
         case PLAN_FOURSTEP: return d.nrows;
         case PLAN_BLUESTEIN: return d.nrows;
@@ -238,7 +240,8 @@ int launch_spectra(rpf_ctx *c, rpf_dev &d, const uint8_t *src, int64_t nspec)
     L.twiddle = d.d_twiddle; L.window = d.d_window; L.rows = d.d_rows;
     L.grid = d.grid; L.stream = d.stream;
     if (c->plan == PLAN_FUSED3) {
-        CU(c, c->use_tc ? rpf_launch_pipe4096_tc(L) : c->usepipe ? rpf_launch_pipe4096(L) : rpf_launch_fused3(c->N, L));
+        CU(c, c->use_tc ? rpf_launch_pipe4096_tc(L) : c->usepipe ? rpf_launch_pipe4096(L)
+              : c->use_pipen ? rpf_launch_pipen(c->N, L) : rpf_launch_fused3(c->N, L));
         d.launches++;
     } else if (c->plan == PLAN_SMALL) {
         CU(c, rpf_launch_small(c->N, L));
@@ -305,7 +308,7 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
             CU(c, rpf_direct_dft_configure());
             break;
         case PLAN_FUSED3:
-            d.grid = c->usepipe ? sms : 2 * sms;
+            d.grid = (c->usepipe || c->use_pipen) ? sms : 2 * sms;
             break;
         case PLAN_SMALL:
             d.grid = 8 * sms;
@@ -357,6 +360,7 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
     if (c->plan == PLAN_FUSED3 || c->plan == PLAN_FOURSTEP) {
         CU(c, rpf_fused3_configure());
         CU(c, rpf_pipe4096_configure());
+        if (c->use_pipen) CU(c, rpf_pipen_configure());
         if (c->use_tc) CU(c, rpf_pipe4096_tc_configure());
     }
     std::vector<float2> tw;
@@ -491,6 +495,11 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             c->plan = PLAN_FUSED3;
             c->usepipe = (N == kInnerN);
             c->use_tc = c->usepipe && !cfg->window && (cfg->flags & RPF_FLAG_TC_PASS1);
+            // measured (B200, Gsamples/s, pipeline / lock-step): 1024: 628 / 607, 2048: 642 / 607, with a window 512: 644 / 606,
+            // 2048: 606 / 556; 512 without a window: 657 / 690 -- every warp owns whole spectra there (no cross-warp
+            // exchange), and the lock-step kernel's 16 warps per SM hide more latency than 8 warps with two streams.
+            c->use_pipen = rpf_pipen_supported(N) && !(cfg->flags & RPF_FLAG_LOCKSTEP) &&
+                           (N != 512 || cfg->window || (cfg->flags & RPF_FLAG_PIPELINE)));
             c->groups = c->usepipe ? 1 : rpf_fused3_groups(N);
         } else if (N <= 256) {
             c->plan = PLAN_SMALL; c->groups = 1;

@@ -22,6 +22,12 @@ int rpf_fused3_groups(int N);          // spectra per CTA iteration (G)
 bool rpf_fused3_supported(int N);
 cudaError_t rpf_fused3_configure();    // opt-in shared memory attributes (once per device)
 
+// N = 512, 1024, 2048: the two-stream pipeline on the generic 3-pass geometry (one CTA per SM): the product path.
+cudaError_t rpf_launch_pipen(int N, const RpfLaunch &L);
+int rpf_pipen_groups(int N);
+bool rpf_pipen_supported(int N);
+cudaError_t rpf_pipen_configure();
+
 // N = 4096, two-stream software pipeline (256-thread CTAs, two spectra per thread): the product path.
 cudaError_t rpf_launch_pipe4096(const RpfLaunch &L);
 cudaError_t rpf_pipe4096_configure();

@@ -27,7 +27,7 @@ CASES = {
     "n1024_linear_baseline_window": (1024, 40, 0x5EED + 1024, 1, 16384 * 5,
                                      ["--linear", "-w", "@hann", "-B", "-"], ["-w", "@hann", "-B", "-"]),
     "n64_three_hops": (64, 500, 77, 2, 16384 * 4, ["--hops", "3"], ["--hops", "3"]),
-    "n2048_straddle": (2048, 30, 31, 0, 16384 * 3, ["--buf-length", str(16384 * 3)], []),
+    "n2048_straddle": (2048, 30, 31, 0, 16384 * 9, ["--buf-length", str(16384 * 3)], []),   # 3 reads of 49,152 bytes
     "n500_bluestein": (500, 40, 0x5EED + 500, 1, 49152, [], []),
 }
 

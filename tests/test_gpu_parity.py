@@ -18,8 +18,8 @@ def stream(nbytes, seed=1, mode=0):
     return pkg.synth_fill_host(nbytes, 0, seed=seed, mode=mode)
 
 
-def run_gpu(N, repeats, chunks, window=None):
-    with Context(N, window=window) as c:
+def run_gpu(N, repeats, chunks, window=None, flags=0):
+    with Context(N, window=window, flags=flags) as c:
         c.reset(repeats)
         for ch in chunks:
             c.push(ch)
@@ -447,6 +447,29 @@ def test_write_data_matches_oracle():
             assert np.allclose(v, vo, rtol=1e-13, atol=1e-13)
         pwr2, _ = c.finish()
         assert np.array_equal(pwr, pwr2)               # write_data leaves the accumulator untouched
+
+
+@pytest.mark.parametrize("N", [512, 1024, 2048])
+@pytest.mark.parametrize("R", [1, 2, 3, 7, 8, 9, 15, 16, 17, 33, 100, 1185, 2371, 4737])
+def test_pipelined_small_bins_tail_shapes(N, R):
+    """N = 512 / 1024 / 2048 run the two-stream pipeline over group iterations of G = 8 / 4 / 2 spectra: counts that
+    leave the last group partial, stream B of the last pair empty, some CTAs with nothing or a single pair, or sit one
+    past a multiple of the grid.  Against the oracle, and against the round-1 lock-step kernel (RPF_FLAG_LOCKSTEP)."""
+    s = stream(2 * N * R, seed=R * 7 + N)
+    pg, done = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_PIPELINE)     # (the default at 512 bins is the lock-step kernel)
+    with Context(N, flags=pkg.capi.RPF_FLAG_LOCKSTEP) as c:
+        c.reset(R)
+        c.push(s)
+        pl, _ = c.finish()
+    Ro = min(R, 300)
+    if Ro == R:
+        po, done_o = ol.oracle_run_stream(N, R, s, buf_length=s.size)
+        assert done == done_o == R
+        assert relmax(pg, po) < TOL
+        assert perbin(pg, po) < (TOL if R >= 9 else 1e-3)
+    assert done == R and relmax(pg, pl) < 2e-6
+    x = s.astype(np.int64) - 127
+    assert pg.sum() == pytest.approx(N * float((x * x).sum()), rel=1e-6)      # nothing lost, nothing counted twice
 
 
 def test_matrix_row_f32_and_smallest_N():
