@@ -499,7 +499,7 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             // 2048: 606 / 556; 512 without a window: 657 / 690 -- every warp owns whole spectra there (no cross-warp
             // exchange), and the lock-step kernel's 16 warps per SM hide more latency than 8 warps with two streams.
             c->use_pipen = rpf_pipen_supported(N) && !(cfg->flags & RPF_FLAG_LOCKSTEP) &&
-                           (N != 512 || cfg->window || (cfg->flags & RPF_FLAG_PIPELINE)));
+                           (N != 512 || cfg->window || (cfg->flags & RPF_FLAG_PIPELINE));
             c->groups = c->usepipe ? 1 : rpf_fused3_groups(N);
         } else if (N <= 256) {
             c->plan = PLAN_SMALL; c->groups = 1;
