@@ -86,9 +86,13 @@ typedef struct rpf_config {
 /* A/B comparisons only (N = 512, 1024, 2048): run the round-1 lock-step kernel (two CTAs per SM, __syncthreads
  * between the passes) instead of the two-stream pipeline. */
 #define RPF_FLAG_LOCKSTEP 4u
-/* A/B comparisons only: force the two-stream pipeline where the lock-step kernel is the default (N = 512 without a
+/* A/B comparisons only: force the two-stream pipeline where the lock-step kernel is the default (N = 2048 without a
  * window). */
 #define RPF_FLAG_PIPELINE 8u
+/* Experiment (N = 65536 without a window): the whole transform in one launch of 16-CTA clusters, the outer radix-16
+ * handed to the inner 4096-point pipelines through distributed shared memory (st.async + remote mbarriers) instead of
+ * a complex64 scratch in HBM.  Same results; measured slower than the default two-kernel path. */
+#define RPF_FLAG_CLUSTER65536 16u
 
 /* Plays the role of fftwf_alloc_complex x2 + fftwf_plan_dft_1d(N, in, out,
  * FFTW_FORWARD, FFTW_MEASURE) in Datastore::Datastore (src/datastore.cxx:30-33):

@@ -10,6 +10,7 @@ RPF_FLAG_TC_PASS1 = 1
 RPF_FLAG_PIPELINED_PUSH = 2
 RPF_FLAG_LOCKSTEP = 4
 RPF_FLAG_PIPELINE = 8
+RPF_FLAG_CLUSTER65536 = 16
 RPF_MAX_DEVICES = 16
 
 EXPORTED_SYMBOLS = [

@@ -25,7 +25,10 @@ namespace {
 
 constexpr int kThreads = 256;                 // compute threads (8 warps)
 constexpr int kLaunchThreads = kThreads + 128;
-constexpr int kStg = 2;                       // TMA ring depth per stream
+#ifndef RPF_PIPEN_STAGES
+#define RPF_PIPEN_STAGES 2
+#endif
+constexpr int kStg = RPF_PIPEN_STAGES;        // TMA ring depth per stream
 constexpr int kIterBytes = 8192;              // G * 2N for every supported N
 constexpr int kFlushPairs = 64;               // flush every 64 loop iterations (= 128 G spectra per CTA)
 constexpr int kHdr = 256;
@@ -54,13 +57,14 @@ struct Geo {
     static_assert(G * 2 * N == kIterBytes, "8 KiB of raw bytes per group iteration");
     static_assert(R1 * R2 * R3 == N, "radix schedule");
 };
-// mbarriers: full[s][slot] (TMA landed) | rc[s] (raw slot consumed: 8 warps + the copy lane) |
+// mbarriers: full[s][slot] (TMA landed) | rc[s][group] (raw slot consumed by one spectrum group: its T/32 warps + the
+// copy lane) |
 // rd[s][e][group] (exchange buffer e of stream s of one spectrum group stored: the T/32 warps of that group only --
 // spectra are independent, so a group never waits for another one; with T = 32 the exchange is warp-local and
 // needs no mbarrier at all)
 __device__ __forceinline__ constexpr int bar_full(int s, int slot) { return s * kStg + slot; }
-__device__ __forceinline__ constexpr int bar_rc(int s) { return 2 * kStg + s; }
-template <int G> __device__ __forceinline__ constexpr int bar_rd(int s, int e, int grp) { return 2 * kStg + 2 + ((s * 2 + (e - 1)) * G + grp); }
+template <int G> __device__ __forceinline__ constexpr int bar_rc(int s, int grp) { return 2 * kStg + s * G + grp; }
+template <int G> __device__ __forceinline__ constexpr int bar_rd(int s, int e, int grp) { return 2 * kStg + 2 * G + ((s * 2 + (e - 1)) * G + grp); }
 
 __device__ __forceinline__ void warp_arrive(uint32_t bar)
 {
@@ -119,10 +123,9 @@ pipen_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__r
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < 2 * kStg; i++) mbar_init(sm + 8 * i, 1);
-        mbar_init(sm + 8 * bar_rc(0), kThreads / 32 + 1);
-        mbar_init(sm + 8 * bar_rc(1), kThreads / 32 + 1);
+        for (int i = 0; i < 2 * G; i++) mbar_init(sm + 8 * (2 * kStg + i), T / 32 + 1);      // rc: the group's warps + the copy lane
         if (!kWarpLocal)
-            for (int i = 0; i < 4 * G; i++) mbar_init(sm + 8 * (2 * kStg + 2 + i), T / 32);
+            for (int i = 0; i < 4 * G; i++) mbar_init(sm + 8 * (2 * kStg + 2 * G + i), T / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -135,11 +138,18 @@ pipen_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__r
             }
             for (int j = 0; j < nit; j++) {
                 const uint32_t ph = (uint32_t)(j & 1);
-                mbar_arrive(sm + 8 * bar_rc(0));
-                mbar_wait(sm + 8 * bar_rc(0), ph);                     // every compute warp has stored its (A,1) rows
+                // Groups are not coupled to each other by the exchange barriers, so "raw slot consumed" is tracked per
+                // group: with one barrier for all eight warps a group that runs an iteration ahead would arrive twice
+                // in one phase and complete it without the slowest group.
+#pragma unroll
+                for (int gq = 0; gq < G; gq++) mbar_arrive(sm + 8 * bar_rc<G>(0, gq));
+#pragma unroll
+                for (int gq = 0; gq < G; gq++) mbar_wait(sm + 8 * bar_rc<G>(0, gq), ph);   // every group has stored its (A,1) rows
                 if (j + kStg <= nit) issue(0, j + kStg);               // ... so A's ring slot is free
-                mbar_arrive(sm + 8 * bar_rc(1));
-                mbar_wait(sm + 8 * bar_rc(1), ph);
+#pragma unroll
+                for (int gq = 0; gq < G; gq++) mbar_arrive(sm + 8 * bar_rc<G>(1, gq));
+#pragma unroll
+                for (int gq = 0; gq < G; gq++) mbar_wait(sm + 8 * bar_rc<G>(1, gq), ph);
                 if (j + kStg < nit) issue(1, j + kStg);
             }
         }
@@ -232,7 +242,7 @@ pipen_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__r
             for (int k1 = 0; k1 < R1; k1++) sts64(s1 + s * g::kS1Bytes + 8 * (k1 * P1 + tau + T * c), v[c * R1 + k1]);
         // the stores above carry values computed from this warp's raw loads, so the ring slot is consumed
         if (kWarpLocal) __syncwarp(); else warp_arrive(sm + 8 * bar_rd<G>(s, 1, grp));
-        if ((tid & 31) == 0) mbar_arrive(sm + 8 * bar_rc(s));
+        if ((tid & 31) == 0) mbar_arrive(sm + 8 * bar_rc<G>(s, grp));
     };
     auto load_s1 = [&](c32 (&v)[16], int s) {
 #pragma unroll

@@ -80,6 +80,7 @@ NcclApi *nccl_api()
 struct rpf_dev {
     int device = 0, sms = 0;
     int grid = 0, nrows = 0;
+    int cluster_grid = 0;             // N = 65536: CTAs of the resident 16-CTA clusters (0: two-kernel four-step path)
     int rows_dirty = 0;               // private accumulator rows written since the last reset
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[kNumStage] = {}, ev_consumed[kNumStage] = {};
@@ -260,6 +261,11 @@ int launch_spectra(rpf_ctx *c, rpf_dev &d, const uint8_t *src, int64_t nspec)
             CU(c, rpf_launch_bluestein(B, src + (size_t)done * c->spectrum_bytes, b, &n));
             d.launches += n;
         }
+    } else if (d.cluster_grid) {
+        RpfLaunch Lc = L;
+        Lc.grid = d.cluster_grid;
+        CU(c, rpf_launch_cluster65536(Lc, d.d_twiddle_big));
+        d.launches++;
     } else {
         for (int64_t done = 0; done < nspec; done += c->scratch_spectra) {
             const int64_t b = (nspec - done) < c->scratch_spectra ? (nspec - done) : c->scratch_spectra;
@@ -354,6 +360,15 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
             fill_twiddle(tb, N);
             CU(c, cudaMalloc(&d.d_twiddle_big, sizeof(float2) * N));
             CU(c, cudaMemcpy(d.d_twiddle_big, tb.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+            // Experiment (RPF_FLAG_CLUSTER65536; 65536 bins, no window): one launch, the outer radix-16 scattered through
+            // distributed shared memory by 16-CTA clusters (cluster65536.cu).  Correct, but 104 against 263 Gsamples/s for the
+            // two-kernel path, so not the default.
+            if (c->M == 16 && !cfg->window && (cfg->flags & RPF_FLAG_CLUSTER65536)) {
+                int ncl = 0;
+                CU(c, rpf_cluster65536_configure(&ncl));
+                if (ncl * 16 > d.grid) ncl = d.grid / 16;          // (rows are sized by d.grid)
+                d.cluster_grid = ncl * 16;
+            }
             break;
         }
     }
@@ -495,11 +510,11 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             c->plan = PLAN_FUSED3;
             c->usepipe = (N == kInnerN);
             c->use_tc = c->usepipe && !cfg->window && (cfg->flags & RPF_FLAG_TC_PASS1);
-            // measured (B200, Gsamples/s, pipeline / lock-step): 1024: 628 / 607, 2048: 642 / 607, with a window 512: 644 / 606,
-            // 2048: 606 / 556; 512 without a window: 657 / 690 -- every warp owns whole spectra there (no cross-warp
-            // exchange), and the lock-step kernel's 16 warps per SM hide more latency than 8 warps with two streams.
+            // measured (B200, Gsamples/s, pipeline / lock-step): 512: 794 / 693, 1024: 611 / 607, 2048: 580 / 607.
+            // At 512 bins every warp owns whole spectra (no cross-warp exchange) and the warps drift apart freely; at 2048
+            // the four warps of a spectrum pair move in step and the lock-step kernel's second CTA per SM hides more.
             c->use_pipen = rpf_pipen_supported(N) && !(cfg->flags & RPF_FLAG_LOCKSTEP) &&
-                           (N != 512 || cfg->window || (cfg->flags & RPF_FLAG_PIPELINE));
+                           (N != 2048 || cfg->window || (cfg->flags & RPF_FLAG_PIPELINE));
             c->groups = c->usepipe ? 1 : rpf_fused3_groups(N);
         } else if (N <= 256) {
             c->plan = PLAN_SMALL; c->groups = 1;

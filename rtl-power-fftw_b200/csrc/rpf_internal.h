@@ -32,6 +32,11 @@ cudaError_t rpf_pipen_configure();
 cudaError_t rpf_launch_pipe4096(const RpfLaunch &L);
 cudaError_t rpf_pipe4096_configure();
 
+// N = 65536 without a window in one launch: 16-CTA clusters, the outer radix-16 handed over through distributed
+// shared memory (st.async + remote mbarriers) instead of a complex64 scratch in HBM.  L.grid = 16 * clusters.
+cudaError_t rpf_cluster65536_configure(int *max_clusters);
+cudaError_t rpf_launch_cluster65536(const RpfLaunch &L, const float2 *twiddle_big);
+
 // N = 4096 with pass 1 on the tensor cores (tcgen05.mma, fp16 hi+lo DFT-16 matrix; raw bytes, no window): experiment
 // selected with RPF_FLAG_TC_PASS1.
 cudaError_t rpf_launch_pipe4096_tc(const RpfLaunch &L);

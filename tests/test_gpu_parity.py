@@ -456,7 +456,7 @@ def test_pipelined_small_bins_tail_shapes(N, R):
     leave the last group partial, stream B of the last pair empty, some CTAs with nothing or a single pair, or sit one
     past a multiple of the grid.  Against the oracle, and against the round-1 lock-step kernel (RPF_FLAG_LOCKSTEP)."""
     s = stream(2 * N * R, seed=R * 7 + N)
-    pg, done = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_PIPELINE)     # (the default at 512 bins is the lock-step kernel)
+    pg, done = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_PIPELINE)     # (forced: the default differs per N)
     with Context(N, flags=pkg.capi.RPF_FLAG_LOCKSTEP) as c:
         c.reset(R)
         c.push(s)
@@ -502,3 +502,24 @@ def test_matrix_row_f32_and_smallest_N():
         assert d2 == 5 and np.all(np.isfinite(v))
         assert v[1] == pytest.approx(p2[0] / d2 / 2 / 1000, rel=1e-12)       # mean of the two neighbours = pwr[0]
         assert v[0] == pytest.approx(p2[0] / d2 / 2 / 1000, rel=1e-12)
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 33, 100, 257])
+def test_cluster65536_matches_two_kernel_path_and_oracle(R):
+    """RPF_FLAG_CLUSTER65536: 65536 bins in one launch of 16-CTA clusters (outer radix-16 handed over through distributed
+    shared memory, csrc/cluster65536.cu; an experiment, not the default).  Spectrum counts that leave clusters idle,
+    stream B of the last pair empty, or the clusters unevenly loaded: against the default two-kernel four-step path (both
+    run the same arithmetic, only the float32 chunking of the accumulation differs), the oracle for small counts,
+    Parseval."""
+    N = 65536
+    s = stream(2 * N * R, seed=R * 13 + 5, mode=1)
+    pc, done = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_CLUSTER65536)
+    pt, done_t = run_gpu(N, R, [s])
+    assert done == done_t == R
+    assert relmax(pc, pt) < 2e-6 and perbin(pc, pt) < 2e-5
+    if R <= 9:
+        po, _ = ol.oracle_run_stream(N, R, s, buf_length=s.size)
+        assert relmax(pc, po) < TOL
+        assert perbin(pc, po) < (TOL if R >= 9 else 1e-3)
+    x = s.astype(np.int64) - 127
+    assert pc.sum() == pytest.approx(N * float((x * x).sum()), rel=1e-6)
