@@ -83,8 +83,9 @@ typedef struct rpf_config {
  * until the next rpf_push / rpf_sync / rpf_finish on this context returns (so two buffers are in flight
  * and the PCIe link never idles between buffers).  Without the flag `bytes` is free on return. */
 #define RPF_FLAG_PIPELINED_PUSH 2u
-/* A/B comparisons only (N = 512, 1024, 2048): run the round-1 lock-step kernel (two CTAs per SM, __syncthreads
- * between the passes) instead of the two-stream pipeline. */
+/* A/B comparisons only: the round-1 kernels -- N = 512, 1024, 2048: the lock-step kernel (two CTAs per SM,
+ * __syncthreads between the passes) instead of the two-stream pipeline; N = 8192 ... 65536: the outer pass with plain
+ * loads and stores instead of the TMA-staged one. */
 #define RPF_FLAG_LOCKSTEP 4u
 /* A/B comparisons only: force the two-stream pipeline where the lock-step kernel is the default (N = 2048 without a
  * window). */

@@ -57,14 +57,14 @@ struct Geo {
     static_assert(G * 2 * N == kIterBytes, "8 KiB of raw bytes per group iteration");
     static_assert(R1 * R2 * R3 == N, "radix schedule");
 };
-// mbarriers: full[s][slot] (TMA landed) | rc[s][group] (raw slot consumed by one spectrum group: its T/32 warps + the
-// copy lane) |
+// mbarriers: full[s][slot] (TMA landed) | empty[s][slot] (raw slot consumed: all 8 warps, once per use of the slot) |
 // rd[s][e][group] (exchange buffer e of stream s of one spectrum group stored: the T/32 warps of that group only --
 // spectra are independent, so a group never waits for another one; with T = 32 the exchange is warp-local and
 // needs no mbarrier at all)
 __device__ __forceinline__ constexpr int bar_full(int s, int slot) { return s * kStg + slot; }
-template <int G> __device__ __forceinline__ constexpr int bar_rc(int s, int grp) { return 2 * kStg + s * G + grp; }
-template <int G> __device__ __forceinline__ constexpr int bar_rd(int s, int e, int grp) { return 2 * kStg + 2 * G + ((s * 2 + (e - 1)) * G + grp); }
+__device__ __forceinline__ constexpr int bar_empty(int s, int slot) { return 2 * kStg + s * kStg + slot; }
+template <int G> __device__ __forceinline__ constexpr int bar_rd(int s, int e, int grp) { return 4 * kStg + ((s * 2 + (e - 1)) * G + grp); }
+static_assert(4 * kStg + 4 * 4 <= kHdr / 8, "mbarriers fit the header (G <= 4 has exchange barriers)");
 
 __device__ __forceinline__ void warp_arrive(uint32_t bar)
 {
@@ -123,9 +123,9 @@ pipen_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__r
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < 2 * kStg; i++) mbar_init(sm + 8 * i, 1);
-        for (int i = 0; i < 2 * G; i++) mbar_init(sm + 8 * (2 * kStg + i), T / 32 + 1);      // rc: the group's warps + the copy lane
+        for (int i = 0; i < 2 * kStg; i++) mbar_init(sm + 8 * (2 * kStg + i), kThreads / 32);     // empty: all eight warps
         if (!kWarpLocal)
-            for (int i = 0; i < 4 * G; i++) mbar_init(sm + 8 * (2 * kStg + 2 * G + i), T / 32);
+            for (int i = 0; i < 4 * G; i++) mbar_init(sm + 8 * (4 * kStg + i), T / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -136,20 +136,17 @@ pipen_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__r
                 if (j <= nit) issue(0, j);
                 if (j < nit) issue(1, j);
             }
+            // Spectrum groups are not coupled to each other by the exchange barriers (with T = 32 nothing couples the
+            // warps at all), so a warp may run more than an iteration ahead of another one.  "Slot consumed" is therefore
+            // one mbarrier PER RING SLOT on which every warp arrives once per use of that slot: a second arrival by the same
+            // warp needs the slot refilled, and it is refilled only after this lane has seen the phase complete -- no
+            // barrier can be completed by the fast warps alone, and the lane cannot miss a phase.
             for (int j = 0; j < nit; j++) {
-                const uint32_t ph = (uint32_t)(j & 1);
-                // Groups are not coupled to each other by the exchange barriers, so "raw slot consumed" is tracked per
-                // group: with one barrier for all eight warps a group that runs an iteration ahead would arrive twice
-                // in one phase and complete it without the slowest group.
-#pragma unroll
-                for (int gq = 0; gq < G; gq++) mbar_arrive(sm + 8 * bar_rc<G>(0, gq));
-#pragma unroll
-                for (int gq = 0; gq < G; gq++) mbar_wait(sm + 8 * bar_rc<G>(0, gq), ph);   // every group has stored its (A,1) rows
+                const int slot = j % kStg;
+                const uint32_t par = (uint32_t)((j / kStg) & 1);
+                mbar_wait(sm + 8 * bar_empty(0, slot), par);           // every warp has stored its (A,1) rows of iteration j
                 if (j + kStg <= nit) issue(0, j + kStg);               // ... so A's ring slot is free
-#pragma unroll
-                for (int gq = 0; gq < G; gq++) mbar_arrive(sm + 8 * bar_rc<G>(1, gq));
-#pragma unroll
-                for (int gq = 0; gq < G; gq++) mbar_wait(sm + 8 * bar_rc<G>(1, gq), ph);
+                mbar_wait(sm + 8 * bar_empty(1, slot), par);
                 if (j + kStg < nit) issue(1, j + kStg);
             }
         }
@@ -227,7 +224,7 @@ pipen_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__r
 #pragma unroll
         for (int c = 0; c < C1; c++) Dft<R1>::run(&v[c * R1]);
     };
-    auto post1 = [&](c32 (&v)[16], int s, auto &&late) {
+    auto post1 = [&](c32 (&v)[16], int s, int slot, auto &&late) {
 #pragma unroll
         for (int c = 0; c < C1; c++) {
             if (!WINDOW)   // remove the R1 * (32768+127) left in output 0 -- exact
@@ -242,7 +239,7 @@ pipen_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__r
             for (int k1 = 0; k1 < R1; k1++) sts64(s1 + s * g::kS1Bytes + 8 * (k1 * P1 + tau + T * c), v[c * R1 + k1]);
         // the stores above carry values computed from this warp's raw loads, so the ring slot is consumed
         if (kWarpLocal) __syncwarp(); else warp_arrive(sm + 8 * bar_rd<G>(s, 1, grp));
-        if ((tid & 31) == 0) mbar_arrive(sm + 8 * bar_rc<G>(s, grp));
+        if ((tid & 31) == 0) mbar_arrive(sm + 8 * bar_empty(s, slot));
     };
     auto load_s1 = [&](c32 (&v)[16], int s) {
 #pragma unroll
@@ -306,7 +303,7 @@ pipen_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__r
         // ---- (A,1)  | prefetch raw B ---------------------------------------------------------
         unpack(vA);
         pass1(vA);
-        post1(vA, 0, [&]() {
+        post1(vA, 0, slot, [&]() {
             mbar_wait(sm + 8 * bar_full(1, slot), (uint32_t)((j / kStg) & 1));
             load_raw(ring + (kStg + slot) * kIterBytes);
         });
@@ -315,7 +312,7 @@ pipen_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__r
         pass1(vB);
         wait_rd(0, 1, ph);
         load_s1(vA, 0);
-        post1(vB, 1, none);
+        post1(vB, 1, slot, none);
         // ---- (A,2)  | prefetch S1[B] ----------------------------------------------------------
         pass2(vA);
         wait_rd(1, 1, ph);

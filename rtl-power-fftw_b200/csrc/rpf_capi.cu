@@ -110,6 +110,7 @@ struct rpf_ctx {
     bool has_window = false;
     bool usepipe = false;             // N=4096 (and the four-step inner transform): pipe4096_kernel
     bool use_tc = false;              // RPF_FLAG_TC_PASS1 and N=4096 without window: pipe4096_tc_kernel
+    bool old_outer = false;           // RPF_FLAG_LOCKSTEP and N > 4096: the round-1 outer-pass kernel (A/B comparisons)
     bool use_pipen = false;           // N = 512, 1024, 2048: pipen_kernel (unless RPF_FLAG_LOCKSTEP)
     bool pipelined = false;           // RPF_FLAG_PIPELINED_PUSH
     int64_t scratch_spectra = 0;
@@ -269,8 +270,8 @@ int launch_spectra(rpf_ctx *c, rpf_dev &d, const uint8_t *src, int64_t nspec)
     } else {
         for (int64_t done = 0; done < nspec; done += c->scratch_spectra) {
             const int64_t b = (nspec - done) < c->scratch_spectra ? (nspec - done) : c->scratch_spectra;
-            CU(c, rpf_launch_fourstep_outer(c->M, src + (size_t)done * c->spectrum_bytes, b, d.d_twiddle_big,
-                                            d.d_window, d.d_scratch, d.sms, d.stream));
+            CU(c, (c->old_outer ? rpf_launch_fourstep_outer : rpf_launch_fourstep_outer_tma)(
+                      c->M, src + (size_t)done * c->spectrum_bytes, b, d.d_twiddle_big, d.d_window, d.d_scratch, d.sms, d.stream));
             RpfLaunch Li = L;
             Li.bytes = nullptr; Li.cplx = d.d_scratch; Li.nspec = b; Li.M = c->M; Li.window = nullptr;
             CU(c, rpf_launch_pipe4096(Li));
@@ -375,6 +376,7 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
     if (c->plan == PLAN_FUSED3 || c->plan == PLAN_FOURSTEP) {
         CU(c, rpf_fused3_configure());
         CU(c, rpf_pipe4096_configure());
+        if (c->plan == PLAN_FOURSTEP) CU(c, rpf_outer_tma_configure());
         if (c->use_pipen) CU(c, rpf_pipen_configure());
         if (c->use_tc) CU(c, rpf_pipe4096_tc_configure());
     }
@@ -520,6 +522,7 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             c->plan = PLAN_SMALL; c->groups = 1;
         } else {
             c->plan = PLAN_FOURSTEP; c->M = N / kInnerN;
+            c->old_outer = (cfg->flags & RPF_FLAG_LOCKSTEP) != 0;
             c->usepipe = true; c->groups = 1;
             const size_t scratch_mb = 256;                            // batch of complex64 rows (measured: 64 -> 171, 256 -> 205 Gs/s)
             c->scratch_spectra = (scratch_mb << 20) / ((size_t)N * sizeof(float2));

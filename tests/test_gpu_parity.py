@@ -523,3 +523,20 @@ def test_cluster65536_matches_two_kernel_path_and_oracle(R):
         assert perbin(pc, po) < (TOL if R >= 9 else 1e-3)
     x = s.astype(np.int64) - 127
     assert pc.sum() == pytest.approx(N * float((x * x).sum()), rel=1e-6)
+
+
+@pytest.mark.parametrize("N,R", [(8192, 37), (16384, 300), (32768, 5), (65536, 1), (65536, 19), (65536, 700)])
+@pytest.mark.parametrize("windowed", [False, True])
+def test_tma_outer_pass_is_bit_identical_to_the_plain_one(N, R, windowed):
+    """The four-step outer pass as a TMA-staged streaming kernel (csrc/outer_tma.cu) performs the arithmetic of the
+    round-1 kernel (RPF_FLAG_LOCKSTEP selects it) in the same order: the spectra must agree bit for bit, for every
+    outer radix, with a window, for counts that leave column ranges without work or cross a scratch batch."""
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32) if windowed else None
+    s = stream(2 * N * R, seed=N + R, mode=1)
+    pn, done = run_gpu(N, R, [s], window=w)
+    po, done_o = run_gpu(N, R, [s], window=w, flags=pkg.capi.RPF_FLAG_LOCKSTEP)
+    assert done == done_o == R
+    assert np.array_equal(pn, po)
+    if R <= 5:
+        pr, _ = ol.oracle_run_stream(N, R, s, window=w, buf_length=s.size)
+        assert relmax(pn, pr) < TOL
