@@ -365,12 +365,13 @@ def bench_config1(pkg, local, reps=300):
             c.reset(R); c.push_ptr(ptr.value, nbytes); pw, done = c.finish()
         dt = (time.perf_counter() - t0) / reps
         launches = c.kernel_launches
+        plan = c.plan_name
     pkg.lib().rpf_host_free(ptr)
     po, done_o = ol.oracle_run_stream(N, R, host, buf_length=nbytes)
     perbin = float(np.max(np.abs(pw - po) / po))
     return {"name": "config1", "bins": N, "spectra": R, "window": None,
             "input": "one 114,688-byte pinned host buffer through rpf_push (12 surplus spectra discarded)",
-            "us_per_integration": dt * 1e6, "Msamples_per_s": R * N / dt / 1e6, "kernel": "fused3_kernel<512>",
+            "us_per_integration": dt * 1e6, "Msamples_per_s": R * N / dt / 1e6, "kernel": "%s_kernel<512> + reduce_rows_kernel" % plan,
             "timing": "host wall clock around rpf_reset + rpf_push + rpf_finish, %d integrations" % reps,
             "parity": {"oracle_perbin": perbin, "repeats_done": int(done), "ok": bool(done == done_o == R and perbin < 1e-5)},
             "launches_total": int(launches)}
@@ -610,7 +611,7 @@ def main():
             configs.append(bench_config_device(pkg, torch, dev, local, "config3", N_BINS, 10000000, hann, 0x5EED + 3, 3,
                                                peak, "pipe4096_kernel<window>"))
             configs.append(bench_config_device(pkg, torch, dev, local, "config4", 65536, 100000, None, 0x5EED + 4, 3,
-                                               peak, "fourstep_outer_kernel<16> + pipe4096_kernel<c32>"))
+                                               peak, "fourstep_outer_tma_kernel<16> + pipe4096_kernel<c32>"))
         else:
             # config 5 as written: 8e7 spectra over 8 GPUs = 1e7 per GPU, one allreduce at the end
             n5 = 10000000

@@ -71,7 +71,9 @@ typedef struct rpf_config {
                                    one Datastore, one pwr[], its spectra dealt over these GPUs and
                                    summed by one NCCL allreduce in rpf_finish (see below)       */
     int32_t      devices[RPF_MAX_DEVICES];
-    int32_t      reserved[4];
+    int32_t      scratch_mib;   /* 0: default.  N = 8192 ... 65536: size of the complex64 scratch between the two
+                                   kernels of the four-step path, i.e. spectra per batch (tuning runs)          */
+    int32_t      reserved[3];
 } rpf_config;
 
 #define RPF_FLAG_NONE 0u
@@ -87,8 +89,7 @@ typedef struct rpf_config {
  * __syncthreads between the passes) instead of the two-stream pipeline; N = 8192 ... 65536: the outer pass with plain
  * loads and stores instead of the TMA-staged one. */
 #define RPF_FLAG_LOCKSTEP 4u
-/* A/B comparisons only: force the two-stream pipeline where the lock-step kernel is the default (N = 2048 without a
- * window). */
+/* A/B comparisons only: force the two-stream pipeline where the lock-step kernel is the default (N = 2048). */
 #define RPF_FLAG_PIPELINE 8u
 /* Experiment (N = 65536 without a window): the whole transform in one launch of 16-CTA clusters, the outer radix-16
  * handed to the inner 4096-point pipelines through distributed shared memory (st.async + remote mbarriers) instead of
@@ -171,8 +172,8 @@ int32_t rpf_device_count(const rpf_ctx *ctx);
 /* Number of this library's kernel launches issued by the context so far. */
 int64_t rpf_kernel_launches(const rpf_ctx *ctx);
 
-/* Name of the kernel family selected for this N ("small", "fused3", "pipe4096_tc", "fourstep", "direct",
- * "bluestein", "gfft"). */
+/* Name of the kernel family selected for this context ("small", "pipen", "fused3", "pipe4096", "pipe4096_tc",
+ * "fourstep", "fourstep_plain_outer", "cluster65536", "direct", "bluestein", "gfft"). */
 const char *rpf_plan_name(const rpf_ctx *ctx);
 
 /* ---- Acquisition::write_data() arithmetic on the device ------------------

@@ -27,7 +27,7 @@ RPF_OK, RPF_ERR_INVALID_ARG, RPF_ERR_UNSUPPORTED_N, RPF_ERR_CUDA, RPF_ERR_NOMEM,
 class RpfConfig(C.Structure):
     _fields_ = [("N", C.c_int32), ("device", C.c_int32), ("window", C.POINTER(C.c_float)),
                 ("buf_length", C.c_int64), ("flags", C.c_uint32), ("n_devices", C.c_int32),
-                ("devices", C.c_int32 * RPF_MAX_DEVICES), ("reserved", C.c_int32 * 4)]
+                ("devices", C.c_int32 * RPF_MAX_DEVICES), ("scratch_mib", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class RpfError(RuntimeError):
@@ -116,11 +116,12 @@ def comm_unique_id():
 class Context:
     """Thin RAII wrapper of rpf_ctx.  Method names follow the C ABI."""
 
-    def __init__(self, N, window=None, device=0, buf_length=0, flags=0, devices=None):
+    def __init__(self, N, window=None, device=0, buf_length=0, flags=0, devices=None, scratch_mib=0):
         self.N = N
         self._h = C.c_void_p()
         cfg = RpfConfig()
         cfg.N, cfg.device, cfg.buf_length, cfg.flags = N, device, buf_length, flags
+        cfg.scratch_mib = scratch_mib
         if devices is not None:
             cfg.n_devices = len(devices)
             for i, d in enumerate(devices):

@@ -26,7 +26,7 @@ namespace {
 constexpr int kThreads = 256;                 // compute threads (8 warps)
 constexpr int kLaunchThreads = kThreads + 128;
 #ifndef RPF_PIPEN_STAGES
-#define RPF_PIPEN_STAGES 2
+#define RPF_PIPEN_STAGES 3             // measured (512 / 1024 / 2048 bins, Gsamples/s): 2 -> 751 / 620 / 547, 3 -> 774 / 620 / 574, 4 -> 762 / 612 / 564
 #endif
 constexpr int kStg = RPF_PIPEN_STAGES;        // TMA ring depth per stream
 constexpr int kIterBytes = 8192;              // G * 2N for every supported N

@@ -93,6 +93,7 @@ struct rpf_dev {
     float *d_window = nullptr;
     double *d_rows = nullptr, *d_pwr = nullptr, *d_tmp = nullptr, *d_baseline = nullptr;
     float2 *d_scratch = nullptr;
+    int64_t scratch_cap = 0;          // spectra the scratch holds now (grows on demand up to rpf_ctx::scratch_spectra)
     float2 *d_chirp = nullptr, *d_bhat = nullptr, *d_blue[2] = {};   // Bluestein tables and ping-pong buffers
     ncclComm_t comm = nullptr;
     int64_t launches = 0;
@@ -268,8 +269,18 @@ int launch_spectra(rpf_ctx *c, rpf_dev &d, const uint8_t *src, int64_t nspec)
         CU(c, rpf_launch_cluster65536(Lc, d.d_twiddle_big));
         d.launches++;
     } else {
-        for (int64_t done = 0; done < nspec; done += c->scratch_spectra) {
-            const int64_t b = (nspec - done) < c->scratch_spectra ? (nspec - done) : c->scratch_spectra;
+        // the complex64 scratch grows with the largest launch seen, up to the batch size: a short integration does not pay
+        // for (or wait on the allocation of) a long one's buffer
+        const int64_t want = nspec < c->scratch_spectra ? nspec : c->scratch_spectra;
+        if (want > d.scratch_cap) {
+            CU(c, cudaStreamSynchronize(d.stream));
+            if (d.d_scratch) CU(c, cudaFree(d.d_scratch));
+            d.d_scratch = nullptr; d.scratch_cap = 0;
+            CU(c, cudaMalloc(&d.d_scratch, (size_t)want * c->N * sizeof(float2)));
+            d.scratch_cap = want;
+        }
+        for (int64_t done = 0; done < nspec; done += d.scratch_cap) {
+            const int64_t b = (nspec - done) < d.scratch_cap ? (nspec - done) : d.scratch_cap;
             CU(c, (c->old_outer ? rpf_launch_fourstep_outer : rpf_launch_fourstep_outer_tma)(
                       c->M, src + (size_t)done * c->spectrum_bytes, b, d.d_twiddle_big, d.d_window, d.d_scratch, d.sms, d.stream));
             RpfLaunch Li = L;
@@ -356,7 +367,6 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
             inner = kInnerN;
             d.grid = (sms / c->M) * c->M;
             if (d.grid < c->M) d.grid = c->M;
-            CU(c, cudaMalloc(&d.d_scratch, (size_t)c->scratch_spectra * N * sizeof(float2)));
             std::vector<float2> tb;
             fill_twiddle(tb, N);
             CU(c, cudaMalloc(&d.d_twiddle_big, sizeof(float2) * N));
@@ -512,11 +522,12 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             c->plan = PLAN_FUSED3;
             c->usepipe = (N == kInnerN);
             c->use_tc = c->usepipe && !cfg->window && (cfg->flags & RPF_FLAG_TC_PASS1);
-            // measured (B200, Gsamples/s, pipeline / lock-step): 512: 794 / 693, 1024: 611 / 607, 2048: 580 / 607.
-            // At 512 bins every warp owns whole spectra (no cross-warp exchange) and the warps drift apart freely; at 2048
-            // the four warps of a spectrum pair move in step and the lock-step kernel's second CTA per SM hides more.
+            // measured (B200, Gsamples/s, pipeline / lock-step): 512: 774 / 693, 1024: 620 / 609, 2048: 574 / 609; with a
+            // window 512: 769 / 606, 1024: 601 / 549, 2048: 556 / 557.  At 512 bins every warp owns whole spectra (no
+            // cross-warp exchange) and the warps drift apart freely; at 2048 the four warps of a spectrum pair move in
+            // step and the lock-step kernel's second CTA per SM hides more.
             c->use_pipen = rpf_pipen_supported(N) && !(cfg->flags & RPF_FLAG_LOCKSTEP) &&
-                           (N != 2048 || cfg->window || (cfg->flags & RPF_FLAG_PIPELINE));
+                           (N != 2048 || (cfg->flags & RPF_FLAG_PIPELINE));
             c->groups = c->usepipe ? 1 : rpf_fused3_groups(N);
         } else if (N <= 256) {
             c->plan = PLAN_SMALL; c->groups = 1;
@@ -524,7 +535,8 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             c->plan = PLAN_FOURSTEP; c->M = N / kInnerN;
             c->old_outer = (cfg->flags & RPF_FLAG_LOCKSTEP) != 0;
             c->usepipe = true; c->groups = 1;
-            const size_t scratch_mb = 256;                            // batch of complex64 rows (measured: 64 -> 171, 256 -> 205 Gs/s)
+            // batch of complex64 rows (round 1: 64 -> 171, 256 -> 205 Gs/s); rpf_config.scratch_mib overrides (tuning runs)
+            const size_t scratch_mb = cfg->scratch_mib > 0 ? (size_t)cfg->scratch_mib : 1024;
             c->scratch_spectra = (scratch_mb << 20) / ((size_t)N * sizeof(float2));
             if (c->scratch_spectra < 1) c->scratch_spectra = 1;
         }
@@ -837,7 +849,10 @@ const char *rpf_plan_name(const rpf_ctx *c)
     if (!c) return "";
     if (c->use_tc) return "pipe4096_tc";
     if (c->plan == PLAN_BLUESTEIN) return c->blueM == c->N ? "gfft" : "bluestein";
-    return c->plan == PLAN_SMALL ? "small" : c->plan == PLAN_FUSED3 ? "fused3" : c->plan == PLAN_DIRECT ? "direct" : "fourstep";
+    if (c->plan == PLAN_FUSED3) return c->usepipe ? "pipe4096" : c->use_pipen ? "pipen" : "fused3";
+    if (c->plan == PLAN_FOURSTEP)
+        return !c->devs.empty() && c->devs[0].cluster_grid ? "cluster65536" : c->old_outer ? "fourstep_plain_outer" : "fourstep";
+    return c->plan == PLAN_SMALL ? "small" : "direct";
 }
 
 int rpf_set_stream(rpf_ctx *c, void *cuda_stream)

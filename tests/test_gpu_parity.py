@@ -308,7 +308,7 @@ def test_linearity_large_config2_shape():
 @pytest.mark.parametrize("N,P,copies", [(65536, 64, 33), (8192, 128, 40), (16384, 64, 40)])
 def test_fourstep_multibatch_single_launch(N, P, copies):
     """The four-step path loops over scratch-sized batches inside ONE rpf_push_device (csrc/rpf_capi.cu,
-    launch_spectra: 512 spectra per batch at 65536 bins, 4096 at 8192): 2112 / 5120 / 2560 spectra in one call
+    launch_spectra; with a 256 MiB scratch: 512 spectra per batch at 65536 bins, 4096 at 8192): 2112 / 5120 / 2560 spectra in one call
     cross 4 / 1 / 1 batch boundaries.  The stream is `copies` repetitions of a P-spectra block, so
     pwr(copies * P spectra) == copies * pwr(P spectra); the P-block itself is pinned to the float64 oracle.
     The equality is not bit-exact here (unlike the repeated-push test below): one big launch partitions the
@@ -317,9 +317,9 @@ def test_fourstep_multibatch_single_launch(N, P, copies):
     block = pkg.synth_fill_host(2 * N * P, 0, seed=0x5EED + 4, mode=1)
     dev = torch.from_numpy(block).cuda().repeat(copies)
     torch.cuda.synchronize()
-    with Context(N) as c:
+    with Context(N, scratch_mib=256) as c:          # (default 1 GiB; 256 MiB keeps the multi-batch case small)
         c.reset(P)
-        c.push_device(dev.data_ptr(), 2 * N * P)
+        c.push_device(dev.data_ptr(), 2 * N * P)    # the scratch is sized for P spectra here and regrown below
         p1, d1 = c.finish()
         c.reset(P * copies)
         l0 = c.kernel_launches
@@ -424,7 +424,7 @@ def test_tc_pass1_variant_kats_and_stream_semantics():
         assert perbin(p, po) < TOL
     w = np.ones(N, np.float32)
     with Context(N, window=w, flags=F) as c:
-        assert c.plan_name == "fused3"                     # with a window the flag is ignored (FP32 kernel)
+        assert c.plan_name == "pipe4096"                   # with a window the flag is ignored (FP32 kernel)
 
 
 def test_write_data_matches_oracle():

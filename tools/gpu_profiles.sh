@@ -29,10 +29,15 @@ with pkg.Context(512) as c:
     for _ in range(6):
         c.reset(100); c.push(s); c.finish()
 " > gpurun_out/prof_config1.log 2>&1
-# sanitizers over the new code paths (tensor-core variant, Bluestein, parallel reduce, multi-batch four-step)
-for tool in memcheck racecheck synccheck; do
-  timeout -s KILL 600 compute-sanitizer --tool $tool python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
-      -k "tc_pass1 or every_even_bin_count or config1 or tail_shapes" > gpurun_out/sanitizer_$tool.txt 2>&1
+# the small-bin pipeline: one full capture each of pipen_kernel<2048> (forced) and pipen_kernel<512>
+timeout -s KILL 200 ncu --set full --clock-control none --import-source on -k regex:pipen_kernel -s 1 -c 1 -f -o gpurun_out/prof_pipen2048 \
+    python tools/kbench.py --n 2048 --mb 1024 --reps 1 --no-check --flags 8 > gpurun_out/prof_pipen2048.log 2>&1
+timeout -s KILL 200 ncu --set full --clock-control none --import-source on -k regex:pipen_kernel -s 1 -c 1 -f -o gpurun_out/prof_pipen512 \
+    python tools/kbench.py --n 512 --mb 1024 --reps 1 --no-check > gpurun_out/prof_pipen512.log 2>&1
+# sanitizers over the round-2 kernels (pipen, TMA outer pass, cluster kernel, tensor-core variant, Bluestein, multi-batch four-step)
+for tool in memcheck synccheck racecheck; do
+  timeout -s KILL 500 compute-sanitizer --tool $tool python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
+      -k "tc_pass1 or every_even_bin_count or config1 or tail_shapes or (tma_outer and 8192) or (cluster65536 and 17)" > gpurun_out/sanitizer_$tool.txt 2>&1
   tail -5 gpurun_out/sanitizer_$tool.txt
 done
 ls -la gpurun_out

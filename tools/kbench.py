@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--window", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--lib", default=None, help="alternative librpf_b200.so (A/B builds under variants/)")
+    ap.add_argument("--scratch-mib", type=int, default=0)
     ap.add_argument("--flags", type=int, default=0, help="rpf_config.flags (1 = RPF_FLAG_TC_PASS1)")
     a = ap.parse_args()
     import torch
@@ -37,7 +38,7 @@ def main():
         w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32) if a.window else None
         with torch.cuda.stream(s):
             pkg.synth_fill_device(dev.data_ptr(), nbytes, 0, seed=1, mode=1, stream=s.cuda_stream)
-            ctx = pkg.Context(N, window=w, flags=a.flags)
+            ctx = pkg.Context(N, window=w, flags=a.flags, scratch_mib=a.scratch_mib)
             ctx.set_stream(s.cuda_stream)
             ts = []
             for i in range(a.reps + 2):
