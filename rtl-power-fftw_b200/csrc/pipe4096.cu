@@ -223,9 +223,17 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) win[n1] = window[n1 * 256 + (tid & (kThreads - 1))];   // (copy-group threads: in range)
     }
+    // RPF_ACC_F64 (experiment): |X|^2 accumulated on the FP64 pipe (2 F2F + 2 DFMA per bin instead of 2 FFMA), no
+    // periodic flush
+#ifdef RPF_ACC_F64
+    double acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = 0.0;
+#else
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) acc[k] = 0.0f;
+#endif
 
     // shared-memory addresses (stream B = +kSpecBytes in the ring, +32 KiB in S1/S2)
     const uint32_t raw_off = 2 * tid;                            // + n1 * 512
@@ -244,7 +252,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 #pragma unroll
         for (int k3 = 0; k3 < 16; k3++) {
             row[(tid + 256 * k3 + kShift) & (kN - 1)] = cur[k3] + (double)acc[k3];   // bin k = tid + 256 k3
-            acc[k3] = 0.0f;
+            acc[k3] = 0;
         }
     };
     c32 vA[16], vB[16];
@@ -277,7 +285,14 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     };
     auto power = [&](const c32 (&v)[16]) {
 #pragma unroll
-        for (int k3 = 0; k3 < 16; k3++) acc[k3] = fmaf(v[k3].x, v[k3].x, fmaf(v[k3].y, v[k3].y, acc[k3]));
+        for (int k3 = 0; k3 < 16; k3++) {
+#ifdef RPF_ACC_F64
+            const double x = (double)v[k3].x, y = (double)v[k3].y;
+            acc[k3] = fma(x, x, fma(y, y, acc[k3]));
+#else
+            acc[k3] = fmaf(v[k3].x, v[k3].x, fmaf(v[k3].y, v[k3].y, acc[k3]));
+#endif
+        }
     };
 
     // pass-1 input of one spectrum from its ring slot: raw bytes (unpacked at the top of the consuming stage)
@@ -366,7 +381,9 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         if (PosRaw::value == 3) fetch_rawA();
         if (haveB) power(vB);
 
+#ifndef RPF_ACC_F64
         if (++since_flush == kFlushPairs) { flush(); since_flush = 0; }
+#endif
     }
     flush();
 }

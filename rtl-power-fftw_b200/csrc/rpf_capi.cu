@@ -372,7 +372,7 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
             CU(c, cudaMalloc(&d.d_twiddle_big, sizeof(float2) * N));
             CU(c, cudaMemcpy(d.d_twiddle_big, tb.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
             // Experiment (RPF_FLAG_CLUSTER65536; 65536 bins, no window): one launch, the outer radix-16 scattered through
-            // distributed shared memory by 16-CTA clusters (cluster65536.cu).  Correct, but 104 against 263 Gsamples/s for the
+            // distributed shared memory by 16-CTA clusters (cluster65536.cu).  Correct, but 212 against 299 Gsamples/s for the
             // two-kernel path, so not the default.
             if (c->M == 16 && !cfg->window && (cfg->flags & RPF_FLAG_CLUSTER65536)) {
                 int ncl = 0;
