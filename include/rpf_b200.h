@@ -85,12 +85,16 @@ typedef struct rpf_config {
  * until the next rpf_push / rpf_sync / rpf_finish on this context returns (so two buffers are in flight
  * and the PCIe link never idles between buffers).  Without the flag `bytes` is free on return. */
 #define RPF_FLAG_PIPELINED_PUSH 2u
-/* A/B comparisons only: the round-1 kernels -- N = 512, 1024, 2048: the lock-step kernel (two CTAs per SM,
- * __syncthreads between the passes) instead of the two-stream pipeline; N = 8192 ... 65536: the outer pass with plain
- * loads and stores instead of the TMA-staged one. */
+/* Kernel choice at N = 512, 1024, 2048 (A/B comparisons; at most one of the three; default: BATCHED4096 at 1024 and
+ * 2048, PIPELINE at 512 -- see the table in rpf_create):
+ *   RPF_FLAG_LOCKSTEP     the round-1 kernel: two CTAs per SM, __syncthreads between the passes.  Also, for
+ *                         N = 8192 ... 65536: the round-1 outer pass (plain loads and stores) instead of the TMA-staged one.
+ *   RPF_FLAG_PIPELINE     the two-stream mbarrier pipeline on the generic three-pass geometry (pipen.cu).
+ *   RPF_FLAG_BATCHED4096  the 4096-bin kernel's loop with 8 / 4 / 2 consecutive spectra per 4096-sample ring slot (pass 1
+ *                         becomes that many radix-2 / 4 / 8 butterflies per thread; passes 2, 3 and both exchanges shared). */
 #define RPF_FLAG_LOCKSTEP 4u
-/* A/B comparisons only: force the two-stream pipeline where the lock-step kernel is the default (N = 2048). */
 #define RPF_FLAG_PIPELINE 8u
+#define RPF_FLAG_BATCHED4096 32u
 /* Experiment (N = 65536 without a window): the whole transform in one launch of 16-CTA clusters, the outer radix-16
  * handed to the inner 4096-point pipelines through distributed shared memory (st.async + remote mbarriers) instead of
  * a complex64 scratch in HBM.  Same results; measured slower than the default two-kernel path. */

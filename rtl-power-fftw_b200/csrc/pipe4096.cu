@@ -119,11 +119,21 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar)
 //   reduce_rows_fourstep() maps (ko, k) -> bin ko + M k.  The complex rows travel through the same TMA ring
 //   as the raw bytes (one 32 KiB bulk copy per row), so the loop is the same for both sources; only the
 //   pass-1 input differs (LDS.64 of complex values instead of LDS.U16 + unpack).
-template <bool WINDOW, bool SRC_C32>
+//
+// Q > 0: N = 4096 >> Q bins (2048, 1024, 512).  A ring slot then holds SPS = 2^Q consecutive spectra, which the same
+//   loop transforms together: with n = 256 a + 16 b + c, a = R1 p + a' (R1 = 16 >> Q), spectrum p of the slot is a
+//   R1 x 16 x 16 transform -- pass 1 becomes SPS radix-R1 butterflies over a' per thread (twiddles W_N^{t k1'}, the same
+//   for every p), row t of S1 holds (p, k1') in place of k1, passes 2 and 3 and both exchanges are UNCHANGED, and thread
+//   (k1 = (p, k1'), k2) ends up with the bins k1' + R1 k2 + 16 R1 k3 of spectrum p: one private accumulator row per
+//   (CTA, p).  `nspec` counts spectra of N bins; the stream's last slot may be partial (fewer bytes are fetched and the
+//   threads of the missing p do not accumulate).
+template <bool WINDOW, bool SRC_C32, int Q = 0>
 __global__ void __launch_bounds__(kLaunchThreads, 1)
 pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx, int64_t nspec, int M,
                 const float2 *__restrict__ twiddle, const float *__restrict__ window, double *__restrict__ rows)
 {
+    static_assert(Q == 0 || !SRC_C32, "batched small transforms read raw bytes");
+    constexpr int SPS = 1 << Q, R1 = 16 >> Q, NB = kN >> Q;     // spectra per slot, pass-1 radix, bins
     using P = Plan<SRC_C32>;
     constexpr int kStg = P::kStg, kSlot = P::kSlot;
     auto bar_full = [](int s, int slot) { return P::bar_full(s, slot); };
@@ -137,6 +147,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     int64_t p0 = 0;
     int nit;
     bool lastB_missing;
+    const int64_t nslots = SRC_C32 ? nspec : (nspec + SPS - 1) / SPS;   // 4096-sample slots in the stream
     const int ko = SRC_C32 ? (int)(blockIdx.x % M) : 0;
     const int part = SRC_C32 ? (int)(blockIdx.x / M) : 0, nparts = SRC_C32 ? (int)(gridDim.x / M) : 1;
     if (SRC_C32) {
@@ -145,12 +156,15 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         nit = (mine + 1) / 2;
         lastB_missing = (mine & 1) != 0;
     } else {
-        const int64_t npairs = (nspec + 1) / 2;
+        const int64_t npairs = (nslots + 1) / 2;
         p0 = (npairs * (int64_t)blockIdx.x) / gridDim.x;
         nit = (int)((npairs * (int64_t)(blockIdx.x + 1)) / gridDim.x - p0);
-        lastB_missing = (p0 + nit) * 2 > nspec;      // stream B of the last pair of the stream may not exist
+        lastB_missing = (p0 + nit) * 2 > nslots;     // stream B of the last pair of the stream may not exist
     }
     if (nit <= 0) return;
+    // Q > 0: the stream's last slot may hold fewer than SPS spectra
+    const int tail_count = (int)(nspec - (nslots - 1) * SPS);            // spectra in the stream's last slot (SPS if full)
+    const bool tail_mine = Q > 0 && tail_count < SPS && (p0 + nit) * 2 >= nslots;   // ... and that slot is one of mine
 
     const uint32_t ring = sm + kHdrP;                            // [stream][slot]
     // ---- TMA: one bulk copy (8 KiB of bytes / 32 KiB complex row) per (stream, iteration) ------
@@ -166,8 +180,9 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         const void *src = SRC_C32 ? (const void *)(cplx + ((size_t)((int64_t)part + (int64_t)nparts * idx) * M + ko) * (size_t)kN)
                                   : (const void *)(cta_bytes + (size_t)idx * kSpecBytes);
         // no proxy fence: the slot was only read through the generic proxy and those loads have completed
-        mbar_expect_tx(bar, kSlot);
-        tma_load_1d(ring + (s * kStg + slot) * kSlot, src, kSlot, bar);
+        const uint32_t nbytes = (tail_mine && idx == last_valid) ? (uint32_t)(tail_count * 2 * NB) : (uint32_t)kSlot;
+        mbar_expect_tx(bar, nbytes);
+        tma_load_1d(ring + (s * kStg + slot) * kSlot, src, nbytes, bar);
     };
     if (tid == 0) {
 #pragma unroll
@@ -215,13 +230,13 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     float2 tw1[15], tw2[15];
 #pragma unroll
     for (int k = 1; k < 16; k++) {
-        tw1[k - 1] = twiddle[(tid * k) & (kN - 1)];             // W_4096^{t k1}, t = tid
+        tw1[k - 1] = twiddle[(tid * k * SPS) & (kN - 1)];       // W_N^{t k1'}, t = tid (only k < R1 is used when Q > 0)
         tw2[k - 1] = twiddle[(hi * k * 16) & (kN - 1)];         // W_256^{n3 k2}, n3 = hi
     }
     float win[WINDOW ? 16 : 1];
     if (WINDOW) {
 #pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) win[n1] = window[n1 * 256 + (tid & (kThreads - 1))];   // (copy-group threads: in range)
+        for (int n1 = 0; n1 < 16; n1++) win[n1] = window[(n1 * 256 + (tid & (kThreads - 1))) & (NB - 1)];   // w[n mod N]
     }
     // RPF_ACC_F64 (experiment): |X|^2 accumulated on the FP64 pipe (2 F2F + 2 DFMA per bin instead of 2 FFMA), no
     // periodic flush
@@ -243,18 +258,21 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     const uint32_t s2_ld = sm + P::kS2 + hi * 2048 + lo * 8;                                             // + n3 * 128
     constexpr uint32_t kStreamS = kN * 8;                        // S1/S2 stream stride
 
-    double *row = rows + (size_t)blockIdx.x * kN;
-    constexpr int kShift = SRC_C32 ? 0 : kN / 2;     // bytes path: fftshift here; four-step: in the reduce kernel
+    // my spectrum of the slot and my first bin: k = k1' + R1 k2 + 16 R1 k3 (Q = 0: tid + 256 k3)
+    const int myp = lo >> (4 - Q), kbase = (lo & (R1 - 1)) + R1 * hi;
+    double *row = rows + ((size_t)blockIdx.x * SPS + myp) * NB;
+    constexpr int kShift = SRC_C32 ? 0 : NB / 2;     // bytes path: fftshift here; four-step: in the reduce kernel
     auto flush = [&]() {
         double cur[16];
 #pragma unroll
-        for (int k3 = 0; k3 < 16; k3++) cur[k3] = row[(tid + 256 * k3 + kShift) & (kN - 1)];
+        for (int k3 = 0; k3 < 16; k3++) cur[k3] = row[(kbase + 16 * R1 * k3 + kShift) & (NB - 1)];
 #pragma unroll
         for (int k3 = 0; k3 < 16; k3++) {
-            row[(tid + 256 * k3 + kShift) & (kN - 1)] = cur[k3] + (double)acc[k3];   // bin k = tid + 256 k3
+            row[(kbase + 16 * R1 * k3 + kShift) & (NB - 1)] = cur[k3] + (double)acc[k3];
             acc[k3] = 0;
         }
     };
+    const bool tail_skip = tail_mine && myp >= tail_count;      // my spectrum of the stream's last slot does not exist
     c32 vA[16], vB[16];
     uint32_t raw[16];
 
@@ -265,13 +283,18 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
             // window: u8 - 127.0f here (exact), the multiplication by w (src/datastore.cxx:76-77) is fused into the
             // first radix-4 layer of pass 1 (dft16_first_windowed)
             if (WINDOW) x = __fadd2_rn(x, make_float2(-kBias, -kBias));
+            if (WINDOW && Q > 0) x = __fmul2_rn(x, make_float2(win[n1], win[n1]));   // (Q = 0: fused into the first radix-4 layer)
             v[n1] = x;
         }
     };
     auto post1 = [&](c32 (&v)[16], int s, auto &&late) {   // bias fix, W_4096^{t k1}, store row t of S1[s], arrive
-        if (!WINDOW && !SRC_C32) v[0] = __fadd2_rn(v[0], make_float2(-16.0f * kBias, -16.0f * kBias));
+        if (!WINDOW && !SRC_C32) {
 #pragma unroll
-        for (int k = 1; k < 16; k++) v[k] = cmul(v[k], tw1[k - 1]);
+            for (int p = 0; p < SPS; p++) v[p * R1] = __fadd2_rn(v[p * R1], make_float2(-(float)R1 * kBias, -(float)R1 * kBias));
+        }
+#pragma unroll
+        for (int k = 1; k < 16; k++)
+            if ((k & (R1 - 1)) != 0) v[k] = cmul(v[k], tw1[(k & (R1 - 1)) - 1]);
         late();
         sts_s1(s1_st + s * kStreamS, v);
         warp_arrive(sm + 8 * bar_rd(s, 1));
@@ -318,6 +341,12 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         auto issuer = [&](bool cond) -> bool { return !RPF_TMAWARP && tid == 0 && cond; };
         auto radix = [&](c32 (&vY)[16], auto pos, auto &&fetch, bool pass1 = false) {
             constexpr int kPos = decltype(pos)::value;
+            if (Q > 0 && pass1) {                    // SPS independent radix-R1 butterflies over a'
+#pragma unroll
+                for (int p = 0; p < SPS; p++) Dft<R1>::run(&vY[p * R1]);
+                if (kPos <= 2) fetch();
+                return;
+            }
             c32 y[16];
             if (WINDOW && !SRC_C32 && pass1) dft16_first_windowed(vY, win); else dft16_first(vY);
             if (kPos == 0) fetch();
@@ -374,12 +403,12 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         // ---- (A,3)  | prefetch S2[B] ----------------------------------------------------------
         radix(vA, PosS2(), fetch_s2B);
         if (PosS2::value == 3) fetch_s2B();
-        power(vA);
+        if (Q == 0 || !(tail_skip && j == nit - 1 && lastB_missing)) power(vA);      // (A is the stream's last slot only then)
 
         // ---- (B,3)  | prefetch raw A of the next iteration ------------------------------------
         radix(vB, PosRaw(), fetch_rawA);
         if (PosRaw::value == 3) fetch_rawA();
-        if (haveB) power(vB);
+        if (haveB && (Q == 0 || !(tail_skip && j == nit - 1))) power(vB);
 
 #ifndef RPF_ACC_F64
         if (++since_flush == kFlushPairs) { flush(); since_flush = 0; }
@@ -396,7 +425,42 @@ cudaError_t rpf_pipe4096_configure()
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(pipe4096_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Plan<false>::kSmem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(pipe4096_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Plan<true>::kSmem);
+    e = cudaFuncSetAttribute(pipe4096_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Plan<true>::kSmem);
+    if (e != cudaSuccess) return e;
+    const void *small[] = {(const void *)pipe4096_kernel<false, false, 1>, (const void *)pipe4096_kernel<true, false, 1>,
+                           (const void *)pipe4096_kernel<false, false, 2>, (const void *)pipe4096_kernel<true, false, 2>,
+                           (const void *)pipe4096_kernel<false, false, 3>, (const void *)pipe4096_kernel<true, false, 3>};
+    for (const void *f : small) {
+        e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Plan<false>::kSmem);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// N = 2048, 1024, 512 on the same loop: 2, 4, 8 spectra per 4096-sample ring slot (template parameter Q).
+template <int Q>
+static cudaError_t launch_small(const RpfLaunch &L)
+{
+    const int64_t nslots = (L.nspec + (1 << Q) - 1) >> Q, npairs = (nslots + 1) / 2;
+    if (npairs <= 0) return cudaSuccess;
+    dim3 grid((unsigned)(npairs < L.grid ? npairs : L.grid)), block(kLaunchThreads);
+    if (L.window)
+        pipe4096_kernel<true, false, Q><<<grid, block, Plan<false>::kSmem, L.stream>>>(L.bytes, nullptr, L.nspec, 1, L.twiddle, L.window, L.rows);
+    else
+        pipe4096_kernel<false, false, Q><<<grid, block, Plan<false>::kSmem, L.stream>>>(L.bytes, nullptr, L.nspec, 1, L.twiddle, nullptr, L.rows);
+    return cudaGetLastError();
+}
+
+bool rpf_pipe4096_small_supported(int N) { return N == 2048 || N == 1024 || N == 512; }
+
+cudaError_t rpf_launch_pipe4096_small(int N, const RpfLaunch &L)
+{
+    switch (N) {
+        case 2048: return launch_small<1>(L);
+        case 1024: return launch_small<2>(L);
+        case 512: return launch_small<3>(L);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t rpf_launch_pipe4096(const RpfLaunch &L)

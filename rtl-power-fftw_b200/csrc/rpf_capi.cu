@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <algorithm>
 #include <new>
 #include <vector>
@@ -33,6 +34,15 @@ constexpr int kDirectMaxN = 128;           // non-power-of-two N up to here: O(N
 constexpr int kBlueSlices = 64;            // private accumulator rows of the Bluestein path (at most)
 
 thread_local char g_create_err[256] = "";
+
+// stdout is the caller's data channel (the reference prints its spectra there, src/acquisition.cxx:391-399).  NCCL prints
+// a version banner to stdout during communicator creation whenever NCCL_DEBUG is set (and ignores NCCL_DEBUG_FILE for
+// it on some versions): while a communicator is being created fd 1 points at stderr.
+struct StdoutToStderr {
+    int saved = -1;
+    StdoutToStderr() { fflush(stdout); saved = dup(1); if (saved >= 0) dup2(2, 1); }
+    ~StdoutToStderr() { if (saved >= 0) { fflush(stdout); dup2(saved, 1); close(saved); } }
+};
 
 // ---- NCCL, resolved at run time ------------------------------------------------------------------
 // Single-GPU use must not require libnccl, and a process that already carries an NCCL (PyTorch bundles
@@ -112,6 +122,7 @@ struct rpf_ctx {
     bool usepipe = false;             // N=4096 (and the four-step inner transform): pipe4096_kernel
     bool use_tc = false;              // RPF_FLAG_TC_PASS1 and N=4096 without window: pipe4096_tc_kernel
     bool old_outer = false;           // RPF_FLAG_LOCKSTEP and N > 4096: the round-1 outer-pass kernel (A/B comparisons)
+    bool use_batched = false;         // N = 512, 1024, 2048 on the pipe4096 loop (4096 / N spectra per ring slot)
     bool use_pipen = false;           // N = 512, 1024, 2048: pipen_kernel (unless RPF_FLAG_LOCKSTEP)
     bool pipelined = false;           // RPF_FLAG_PIPELINED_PUSH
     int64_t scratch_spectra = 0;
@@ -223,7 +234,7 @@ int rows_touched(const rpf_ctx *c, const rpf_dev &d, int64_t nspec)
     switch (c->plan) {
         case PLAN_FUSED3:
             blocks = c->usepipe ? (nspec + 1) / 2 : (nspec + c->groups - 1) / c->groups;
-            if (c->use_pipen) blocks = (blocks + 1) / 2;               // pairs of group iterations
+            if (c->use_pipen || c->use_batched) blocks = (blocks + 1) / 2;   // pairs of group iterations / ring slots
             break;
         case PLAN_FOURSTEP: return d.nrows;
         case PLAN_BLUESTEIN: return d.nrows;
@@ -244,6 +255,7 @@ int launch_spectra(rpf_ctx *c, rpf_dev &d, const uint8_t *src, int64_t nspec)
     L.grid = d.grid; L.stream = d.stream;
     if (c->plan == PLAN_FUSED3) {
         CU(c, c->use_tc ? rpf_launch_pipe4096_tc(L) : c->usepipe ? rpf_launch_pipe4096(L)
+              : c->use_batched ? rpf_launch_pipe4096_small(c->N, L)
               : c->use_pipen ? rpf_launch_pipen(c->N, L) : rpf_launch_fused3(c->N, L));
         d.launches++;
     } else if (c->plan == PLAN_SMALL) {
@@ -326,7 +338,8 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
             CU(c, rpf_direct_dft_configure());
             break;
         case PLAN_FUSED3:
-            d.grid = (c->usepipe || c->use_pipen) ? sms : 2 * sms;
+            d.grid = (c->usepipe || c->use_pipen || c->use_batched) ? sms : 2 * sms;
+            if (c->use_batched) inner = kInnerN;                 // the loop's twiddles come from the W_4096 table
             break;
         case PLAN_SMALL:
             d.grid = 8 * sms;
@@ -522,13 +535,18 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             c->plan = PLAN_FUSED3;
             c->usepipe = (N == kInnerN);
             c->use_tc = c->usepipe && !cfg->window && (cfg->flags & RPF_FLAG_TC_PASS1);
-            // measured (B200, Gsamples/s, pipeline / lock-step): 512: 774 / 693, 1024: 620 / 609, 2048: 574 / 609; with a
-            // window 512: 769 / 606, 1024: 601 / 549, 2048: 556 / 557.  At 512 bins every warp owns whole spectra (no
-            // cross-warp exchange) and the warps drift apart freely; at 2048 the four warps of a spectrum pair move in
-            // step and the lock-step kernel's second CTA per SM hides more.
-            c->use_pipen = rpf_pipen_supported(N) && !(cfg->flags & RPF_FLAG_LOCKSTEP) &&
-                           (N != 2048 || (cfg->flags & RPF_FLAG_PIPELINE));
-            c->groups = c->usepipe ? 1 : rpf_fused3_groups(N);
+            // Three kernels cover 512 / 1024 / 2048 bins; measured on the B200 (Gsamples/s; with a Hann window in brackets):
+            //                     512          1024         2048
+            //   batched on the    693 (695)    716 (671)    661 (641)    4096 loop, 8 / 4 / 2 spectra per ring slot
+            //   pipen             774 (768)    621 (601)    574 (556)    two-stream pipeline, exchange barriers per spectrum
+            //   fused3            693 (606)    609 (549)    609 (557)    lock-step, two CTAs per SM (round 1)
+            // At 512 bins every warp of pipen owns whole spectra (no cross-warp exchange) and the warps drift apart
+            // freely; above that the tuned 4096 loop wins.  The flags force a kernel for A/B runs.
+            const uint32_t forced = cfg->flags & (RPF_FLAG_LOCKSTEP | RPF_FLAG_PIPELINE | RPF_FLAG_BATCHED4096);
+            const bool small = rpf_pipen_supported(N);
+            c->use_batched = small && (forced ? forced == RPF_FLAG_BATCHED4096 : N != 512);
+            c->use_pipen = small && (forced ? forced == RPF_FLAG_PIPELINE : N == 512);
+            c->groups = c->usepipe ? 1 : c->use_batched ? kInnerN / N : rpf_fused3_groups(N);
         } else if (N <= 256) {
             c->plan = PLAN_SMALL; c->groups = 1;
         } else {
@@ -557,7 +575,10 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             std::vector<ncclComm_t> comms(nd);
             std::vector<int> ids(nd);
             for (int i = 0; i < nd; i++) ids[i] = c->devs[i].device;
-            NC(c, api, api->CommInitAll(comms.data(), nd, ids.data()));
+            {
+                StdoutToStderr guard;
+                NC(c, api, api->CommInitAll(comms.data(), nd, ids.data()));
+            }
             for (int i = 0; i < nd; i++) c->devs[i].comm = comms[i];
         }
         return RPF_OK;
@@ -849,7 +870,7 @@ const char *rpf_plan_name(const rpf_ctx *c)
     if (!c) return "";
     if (c->use_tc) return "pipe4096_tc";
     if (c->plan == PLAN_BLUESTEIN) return c->blueM == c->N ? "gfft" : "bluestein";
-    if (c->plan == PLAN_FUSED3) return c->usepipe ? "pipe4096" : c->use_pipen ? "pipen" : "fused3";
+    if (c->plan == PLAN_FUSED3) return c->usepipe ? "pipe4096" : c->use_batched ? "pipe4096_batched" : c->use_pipen ? "pipen" : "fused3";
     if (c->plan == PLAN_FOURSTEP)
         return !c->devs.empty() && c->devs[0].cluster_grid ? "cluster65536" : c->old_outer ? "fourstep_plain_outer" : "fourstep";
     return c->plan == PLAN_SMALL ? "small" : "direct";
@@ -895,7 +916,10 @@ int rpf_comm_init_rank(rpf_ctx *c, const void *id, size_t id_bytes, int32_t rank
     if (d.comm) { api->CommDestroy(d.comm); d.comm = nullptr; }
     ncclUniqueId uid;
     memcpy(&uid, id, sizeof(uid));
-    NC(c, api, api->CommInitRank(&d.comm, nranks, uid, rank));
+    {
+        StdoutToStderr guard;
+        NC(c, api, api->CommInitRank(&d.comm, nranks, uid, rank));
+    }
     c->comm_rank = rank; c->comm_nranks = nranks;
     return RPF_OK;
 }

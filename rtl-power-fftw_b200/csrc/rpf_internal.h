@@ -32,6 +32,12 @@ cudaError_t rpf_pipen_configure();
 cudaError_t rpf_launch_pipe4096(const RpfLaunch &L);
 cudaError_t rpf_pipe4096_configure();
 
+// N = 2048 / 1024 / 512 on the pipe4096 loop: 2 / 4 / 8 consecutive spectra share a 4096-sample ring slot, pass 1 runs that
+// many radix-8 / 4 / 2 butterflies per thread, passes 2 and 3 are the 4096 kernel's.  L.twiddle = the W_4096 table,
+// L.rows = (4096 / N) private rows of N doubles per CTA.
+bool rpf_pipe4096_small_supported(int N);
+cudaError_t rpf_launch_pipe4096_small(int N, const RpfLaunch &L);
+
 // N = 65536 without a window in one launch: 16-CTA clusters, the outer radix-16 handed over through distributed
 // shared memory (st.async + remote mbarriers) instead of a complex64 scratch in HBM.  L.grid = 16 * clusters.
 cudaError_t rpf_cluster65536_configure(int *max_clusters);

@@ -540,3 +540,51 @@ def test_tma_outer_pass_is_bit_identical_to_the_plain_one(N, R, windowed):
     if R <= 5:
         pr, _ = ol.oracle_run_stream(N, R, s, window=w, buf_length=s.size)
         assert relmax(pn, pr) < TOL
+
+
+@pytest.mark.parametrize("N", [512, 1024, 2048])
+@pytest.mark.parametrize("R", [1, 2, 3, 7, 8, 9, 15, 16, 17, 33, 100, 1185, 2371, 4737])
+def test_batched_small_bins_on_the_4096_loop(N, R):
+    """RPF_FLAG_BATCHED4096: 512 / 1024 / 2048 bins run on the 4096-bin kernel's loop with 8 / 4 / 2 consecutive spectra
+    per ring slot.  Spectrum counts that leave the stream's last slot partial (only some of its spectra exist), stream B
+    of the last pair empty, CTAs with nothing or a single pair: against the oracle, the lock-step kernel, Parseval."""
+    F = pkg.capi.RPF_FLAG_BATCHED4096
+    s = stream(2 * N * R, seed=R * 11 + N)
+    with Context(N, flags=F) as c:
+        assert c.plan_name == "pipe4096_batched"
+        c.reset(R)
+        c.push(s)
+        pg, done = c.finish()
+    pl, _ = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_LOCKSTEP)
+    if R <= 300:
+        po, done_o = ol.oracle_run_stream(N, R, s, buf_length=s.size)
+        assert done == done_o == R
+        assert relmax(pg, po) < TOL
+        assert perbin(pg, po) < (TOL if R >= 9 else 1e-3)
+    assert done == R and relmax(pg, pl) < 2e-6
+    x = s.astype(np.int64) - 127
+    assert pg.sum() == pytest.approx(N * float((x * x).sum()), rel=1e-6)      # nothing lost, nothing counted twice
+
+
+@pytest.mark.parametrize("N", [512, 1024, 2048])
+def test_batched_small_bins_window_kats_and_straddling_pushes(N):
+    """The same path with a Hann window, the analytic KATs (tone bin, zero input), and odd-sized pushes that straddle
+    spectra and ring slots (the carry is resolved on the host, so every launch starts on a spectrum boundary -- but not
+    on a slot boundary of the stream: slots are per launch)."""
+    F = pkg.capi.RPF_FLAG_BATCHED4096
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32)
+    R = 37
+    s = stream(2 * N * R, seed=N + 3, mode=1)
+    pg, done = run_gpu(N, R, [s], window=w, flags=F)
+    po, _ = ol.oracle_run_stream(N, R, s, window=w, buf_length=s.size)
+    assert done == R and relmax(pg, po) < TOL and perbin(pg, po) < TOL
+    t = stream(2 * N * 12, seed=5, mode=2)                                   # tone at +fs/8
+    pt, _ = run_gpu(N, 12, [t], flags=F)
+    assert int(np.argmax(pt)) == N // 2 + N // 8
+    z = np.full(2 * N * 5, 127, np.uint8)
+    pz, _ = run_gpu(N, 5, [z], flags=F)
+    assert np.all(pz == 0.0)
+    chunks = [s[i:i + 10006] for i in range(0, s.size, 10006)]
+    pc, done_c = run_gpu(N, R, chunks, flags=F)
+    pw, _ = run_gpu(N, R, [s], flags=F)
+    assert done_c == R and relmax(pc, pw) < 2e-6
