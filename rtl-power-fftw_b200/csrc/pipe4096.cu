@@ -126,14 +126,20 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar)
 //   for every p), row t of S1 holds (p, k1') in place of k1, passes 2 and 3 and both exchanges are UNCHANGED, and thread
 //   (k1 = (p, k1'), k2) ends up with the bins k1' + R1 k2 + 16 R1 k3 of spectrum p: one private accumulator row per
 //   (CTA, p).  `nspec` counts spectra of N bins; the stream's last slot may be partial (fewer bytes are fetched and the
-//   threads of the missing p do not accumulate).
+//   threads of the missing p do not accumulate).  Q > 4 (N = 128 ... 16) repeats the step on the second digit: pass 1
+//   is empty, b = R2 pb + b' (R2 = 16 >> (Q - 4)), pass 2 becomes 16 / R2 radix-R2 butterflies with twiddles
+//   W_N^{c k2'}, and thread (k1, k2 = (pb, k2')) holds bins k2' + R2 k3 of spectrum (16 / R2) k1 + pb.
 template <bool WINDOW, bool SRC_C32, int Q = 0>
 __global__ void __launch_bounds__(kLaunchThreads, 1)
 pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cplx, int64_t nspec, int M,
                 const float2 *__restrict__ twiddle, const float *__restrict__ window, double *__restrict__ rows)
 {
     static_assert(Q == 0 || !SRC_C32, "batched small transforms read raw bytes");
-    constexpr int SPS = 1 << Q, R1 = 16 >> Q, NB = kN >> Q;     // spectra per slot, pass-1 radix, bins
+    static_assert(Q >= 0 && Q <= 8, "N = 4096 >> Q, 16 <= N <= 4096");
+    constexpr int SPS = 1 << Q, NB = kN >> Q;                      // spectra per slot, bins
+    constexpr int R1 = Q < 4 ? 16 >> Q : 1;                         // radix of pass 1 (over a')
+    constexpr int R2 = Q <= 4 ? 16 : 16 >> (Q - 4);                 // radix of pass 2 (over b'); pass 3 is always radix 16
+    constexpr int L1 = Q < 4 ? 4 - Q : 0, L2 = Q <= 4 ? 4 : 8 - Q;  // log2 R1, log2 R2
     using P = Plan<SRC_C32>;
     constexpr int kStg = P::kStg, kSlot = P::kSlot;
     auto bar_full = [](int s, int slot) { return P::bar_full(s, slot); };
@@ -231,7 +237,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 #pragma unroll
     for (int k = 1; k < 16; k++) {
         tw1[k - 1] = twiddle[(tid * k * SPS) & (kN - 1)];       // W_N^{t k1'}, t = tid (only k < R1 is used when Q > 0)
-        tw2[k - 1] = twiddle[(hi * k * 16) & (kN - 1)];         // W_256^{n3 k2}, n3 = hi
+        tw2[k - 1] = twiddle[(hi * k * (kN / (16 * R2))) & (kN - 1)];   // W_{16 R2}^{n3 k2'}, n3 = hi (W_256^{n3 k2} unless Q > 4)
     }
     float win[WINDOW ? 16 : 1];
     if (WINDOW) {
@@ -258,17 +264,17 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     const uint32_t s2_ld = sm + P::kS2 + hi * 2048 + lo * 8;                                             // + n3 * 128
     constexpr uint32_t kStreamS = kN * 8;                        // S1/S2 stream stride
 
-    // my spectrum of the slot and my first bin: k = k1' + R1 k2 + 16 R1 k3 (Q = 0: tid + 256 k3)
-    const int myp = lo >> (4 - Q), kbase = (lo & (R1 - 1)) + R1 * hi;
+    // my spectrum of the slot and my first bin: k = k1' + R1 (k2' + R2 k3)   (Q = 0: tid + 256 k3)
+    const int myp = ((lo >> L1) << (4 - L2)) + (hi >> L2), kbase = (lo & (R1 - 1)) + R1 * (hi & (R2 - 1));
     double *row = rows + ((size_t)blockIdx.x * SPS + myp) * NB;
     constexpr int kShift = SRC_C32 ? 0 : NB / 2;     // bytes path: fftshift here; four-step: in the reduce kernel
     auto flush = [&]() {
         double cur[16];
 #pragma unroll
-        for (int k3 = 0; k3 < 16; k3++) cur[k3] = row[(kbase + 16 * R1 * k3 + kShift) & (NB - 1)];
+        for (int k3 = 0; k3 < 16; k3++) cur[k3] = row[(kbase + R2 * R1 * k3 + kShift) & (NB - 1)];
 #pragma unroll
         for (int k3 = 0; k3 < 16; k3++) {
-            row[(kbase + 16 * R1 * k3 + kShift) & (NB - 1)] = cur[k3] + (double)acc[k3];
+            row[(kbase + R2 * R1 * k3 + kShift) & (NB - 1)] = cur[k3] + (double)acc[k3];
             acc[k3] = 0;
         }
     };
@@ -290,7 +296,7 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     auto post1 = [&](c32 (&v)[16], int s, auto &&late) {   // bias fix, W_4096^{t k1}, store row t of S1[s], arrive
         if (!WINDOW && !SRC_C32) {
 #pragma unroll
-            for (int p = 0; p < SPS; p++) v[p * R1] = __fadd2_rn(v[p * R1], make_float2(-(float)R1 * kBias, -(float)R1 * kBias));
+            for (int p = 0; p < 16 / R1; p++) v[p * R1] = __fadd2_rn(v[p * R1], make_float2(-(float)R1 * kBias, -(float)R1 * kBias));
         }
 #pragma unroll
         for (int k = 1; k < 16; k++)
@@ -301,7 +307,8 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
     };
     auto post2 = [&](c32 (&v)[16], int s, auto &&late) {   // W_256^{n3 k2}, store S2[s], arrive
 #pragma unroll
-        for (int k = 1; k < 16; k++) v[k] = cmul(v[k], tw2[k - 1]);
+        for (int k = 1; k < 16; k++)
+            if ((k & (R2 - 1)) != 0) v[k] = cmul(v[k], tw2[(k & (R2 - 1)) - 1]);
         late();
         sts_s2(s2_st + s * kStreamS, v);
         warp_arrive(sm + 8 * bar_rd(s, 2));
@@ -339,11 +346,18 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
         // RPF_TMAWARP = 0 only: thread 0 issues the bulk copies inside the loop (a warp-uniform branch with elect.sync
         // was measured 14 % slower)
         auto issuer = [&](bool cond) -> bool { return !RPF_TMAWARP && tid == 0 && cond; };
-        auto radix = [&](c32 (&vY)[16], auto pos, auto &&fetch, bool pass1 = false) {
+        auto radix = [&](c32 (&vY)[16], auto pos, auto &&fetch, int pass = 3) {
             constexpr int kPos = decltype(pos)::value;
-            if (Q > 0 && pass1) {                    // SPS independent radix-R1 butterflies over a'
+            const bool pass1 = pass == 1;
+            if (Q > 0 && pass == 1) {                // 16 / R1 independent radix-R1 butterflies over a'
 #pragma unroll
-                for (int p = 0; p < SPS; p++) Dft<R1>::run(&vY[p * R1]);
+                for (int p = 0; p < 16 / R1; p++) Dft<R1>::run(&vY[p * R1]);
+                if (kPos <= 2) fetch();
+                return;
+            }
+            if (Q > 4 && pass == 2) {                // 16 / R2 independent radix-R2 butterflies over b'
+#pragma unroll
+                for (int p = 0; p < 16 / R2; p++) Dft<R2>::run(&vY[p * R2]);
                 if (kPos <= 2) fetch();
                 return;
             }
@@ -384,20 +398,20 @@ pipe4096_kernel(const uint8_t *__restrict__ bytes, const float2 *__restrict__ cp
 
         // ---- (A,1)  | prefetch raw B ---------------------------------------------------------
         if (!SRC_C32) unpack(vA);
-        radix(vA, PosRaw(), fetch_rawB, true);
+        radix(vA, PosRaw(), fetch_rawB, 1);
         if (PosRaw::value == 3) post1(vA, 0, fetch_rawB); else post1(vA, 0, none);
 
         // ---- (B,1)  | prefetch S1[A] ----------------------------------------------------------
         if (!SRC_C32) unpack(vB);
-        radix(vB, PosS1(), fetch_s1A, true);
+        radix(vB, PosS1(), fetch_s1A, 1);
         if (PosS1::value == 3) post1(vB, 1, fetch_s1A); else post1(vB, 1, none);
 
         // ---- (A,2)  | prefetch S1[B] ----------------------------------------------------------
-        radix(vA, PosS1(), fetch_s1B);
+        radix(vA, PosS1(), fetch_s1B, 2);
         if (PosS1::value == 3) post2(vA, 0, fetch_s1B); else post2(vA, 0, none);
 
         // ---- (B,2)  | prefetch S2[A] ----------------------------------------------------------
-        radix(vB, PosS2(), fetch_s2A);
+        radix(vB, PosS2(), fetch_s2A, 2);
         if (PosS2::value == 3) post2(vB, 1, fetch_s2A); else post2(vB, 1, none);
 
         // ---- (A,3)  | prefetch S2[B] ----------------------------------------------------------
@@ -429,7 +443,12 @@ cudaError_t rpf_pipe4096_configure()
     if (e != cudaSuccess) return e;
     const void *small[] = {(const void *)pipe4096_kernel<false, false, 1>, (const void *)pipe4096_kernel<true, false, 1>,
                            (const void *)pipe4096_kernel<false, false, 2>, (const void *)pipe4096_kernel<true, false, 2>,
-                           (const void *)pipe4096_kernel<false, false, 3>, (const void *)pipe4096_kernel<true, false, 3>};
+                           (const void *)pipe4096_kernel<false, false, 3>, (const void *)pipe4096_kernel<true, false, 3>,
+                           (const void *)pipe4096_kernel<false, false, 4>, (const void *)pipe4096_kernel<true, false, 4>,
+                           (const void *)pipe4096_kernel<false, false, 5>, (const void *)pipe4096_kernel<true, false, 5>,
+                           (const void *)pipe4096_kernel<false, false, 6>, (const void *)pipe4096_kernel<true, false, 6>,
+                           (const void *)pipe4096_kernel<false, false, 7>, (const void *)pipe4096_kernel<true, false, 7>,
+                           (const void *)pipe4096_kernel<false, false, 8>, (const void *)pipe4096_kernel<true, false, 8>};
     for (const void *f : small) {
         e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Plan<false>::kSmem);
         if (e != cudaSuccess) return e;
@@ -437,7 +456,7 @@ cudaError_t rpf_pipe4096_configure()
     return cudaSuccess;
 }
 
-// N = 2048, 1024, 512 on the same loop: 2, 4, 8 spectra per 4096-sample ring slot (template parameter Q).
+// N = 2048 ... 16 on the same loop: 2 ... 256 spectra per 4096-sample ring slot (template parameter Q).
 template <int Q>
 static cudaError_t launch_small(const RpfLaunch &L)
 {
@@ -451,7 +470,7 @@ static cudaError_t launch_small(const RpfLaunch &L)
     return cudaGetLastError();
 }
 
-bool rpf_pipe4096_small_supported(int N) { return N == 2048 || N == 1024 || N == 512; }
+bool rpf_pipe4096_small_supported(int N) { return N >= 16 && N <= 2048 && (N & (N - 1)) == 0; }
 
 cudaError_t rpf_launch_pipe4096_small(int N, const RpfLaunch &L)
 {
@@ -459,6 +478,11 @@ cudaError_t rpf_launch_pipe4096_small(int N, const RpfLaunch &L)
         case 2048: return launch_small<1>(L);
         case 1024: return launch_small<2>(L);
         case 512: return launch_small<3>(L);
+        case 256: return launch_small<4>(L);       // 16 x 16: pass 1 is empty (R1 = 1)
+        case 128: return launch_small<5>(L);       // 8 x 16
+        case 64: return launch_small<6>(L);        // 4 x 16
+        case 32: return launch_small<7>(L);        // 2 x 16
+        case 16: return launch_small<8>(L);        // pass 3 only
         default: return cudaErrorInvalidValue;
     }
 }

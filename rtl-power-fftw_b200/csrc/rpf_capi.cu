@@ -547,6 +547,10 @@ int rpf_create(const rpf_config *cfg, rpf_ctx **out)
             c->use_batched = small && (forced ? forced == RPF_FLAG_BATCHED4096 : N != 512);
             c->use_pipen = small && (forced ? forced == RPF_FLAG_PIPELINE : N == 512);
             c->groups = c->usepipe ? 1 : c->use_batched ? kInnerN / N : rpf_fused3_groups(N);
+        } else if (N >= 16 && N <= 256 && !(cfg->flags & RPF_FLAG_LOCKSTEP)) {
+            // 256 ... 16 bins: the 4096 loop with 16 ... 256 spectra per ring slot, pass 1 (and part of pass 2) empty:
+            // 722 Gsamples/s at 256 bins against 60 for small_kernel (RPF_FLAG_LOCKSTEP selects it for A/B runs)
+            c->plan = PLAN_FUSED3; c->use_batched = true; c->groups = kInnerN / N;
         } else if (N <= 256) {
             c->plan = PLAN_SMALL; c->groups = 1;
         } else {

@@ -542,11 +542,12 @@ def test_tma_outer_pass_is_bit_identical_to_the_plain_one(N, R, windowed):
         assert relmax(pn, pr) < TOL
 
 
-@pytest.mark.parametrize("N", [512, 1024, 2048])
-@pytest.mark.parametrize("R", [1, 2, 3, 7, 8, 9, 15, 16, 17, 33, 100, 1185, 2371, 4737])
+@pytest.mark.parametrize("N", [16, 32, 64, 128, 256, 512, 1024, 2048])
+@pytest.mark.parametrize("R", [1, 2, 3, 7, 8, 9, 15, 16, 17, 33, 100, 1185, 2371, 4737, 75777])
 def test_batched_small_bins_on_the_4096_loop(N, R):
-    """RPF_FLAG_BATCHED4096: 512 / 1024 / 2048 bins run on the 4096-bin kernel's loop with 8 / 4 / 2 consecutive spectra
-    per ring slot.  Spectrum counts that leave the stream's last slot partial (only some of its spectra exist), stream B
+    """RPF_FLAG_BATCHED4096 (the default from 16 to 256 and at 1024 / 2048 bins): N bins run on the 4096-bin kernel's loop
+    with 4096 / N consecutive spectra per ring slot (N <= 256: pass 1 is empty; N < 256: pass 2 is 16 / R2 radix-R2
+    butterflies).  Spectrum counts that leave the stream's last slot partial (only some of its spectra exist), stream B
     of the last pair empty, CTAs with nothing or a single pair: against the oracle, the lock-step kernel, Parseval."""
     F = pkg.capi.RPF_FLAG_BATCHED4096
     s = stream(2 * N * R, seed=R * 11 + N)
@@ -566,7 +567,7 @@ def test_batched_small_bins_on_the_4096_loop(N, R):
     assert pg.sum() == pytest.approx(N * float((x * x).sum()), rel=1e-6)      # nothing lost, nothing counted twice
 
 
-@pytest.mark.parametrize("N", [512, 1024, 2048])
+@pytest.mark.parametrize("N", [16, 32, 64, 128, 256, 512, 1024, 2048])
 def test_batched_small_bins_window_kats_and_straddling_pushes(N):
     """The same path with a Hann window, the analytic KATs (tone bin, zero input), and odd-sized pushes that straddle
     spectra and ring slots (the carry is resolved on the host, so every launch starts on a spectrum boundary -- but not
