@@ -91,6 +91,8 @@ struct rpf_dev {
     int device = 0, sms = 0;
     int grid = 0, nrows = 0;
     int cluster_grid = 0;             // N = 65536: CTAs of the resident 16-CTA clusters (0: two-kernel four-step path)
+    int solo_grid = 0;                // N = 65536: CTAs of the one-CTA-per-spectrum kernel (0: not selected)
+    float2 *d_solo = nullptr;         // ... and their private scratch, 512 KiB each
     int rows_dirty = 0;               // private accumulator rows written since the last reset
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[kNumStage] = {}, ev_consumed[kNumStage] = {};
@@ -275,6 +277,11 @@ int launch_spectra(rpf_ctx *c, rpf_dev &d, const uint8_t *src, int64_t nspec)
             CU(c, rpf_launch_bluestein(B, src + (size_t)done * c->spectrum_bytes, b, &n));
             d.launches += n;
         }
+    } else if (d.solo_grid) {
+        RpfLaunch Ls = L;
+        Ls.grid = d.solo_grid;
+        CU(c, rpf_launch_solo65536(Ls, d.d_twiddle_big, d.d_solo));
+        d.launches++;
     } else if (d.cluster_grid) {
         RpfLaunch Lc = L;
         Lc.grid = d.cluster_grid;
@@ -392,6 +399,15 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
                 CU(c, rpf_cluster65536_configure(&ncl));
                 if (ncl * 16 > d.grid) ncl = d.grid / 16;          // (rows are sized by d.grid)
                 d.cluster_grid = ncl * 16;
+            }
+            // RPF_FLAG_SOLO65536 (65536 bins, no window): one launch, one CTA per spectrum (solo65536.cu)
+            if (c->M == 16 && !cfg->window && (cfg->flags & RPF_FLAG_SOLO65536)) {
+                CU(c, rpf_solo65536_configure());
+                d.solo_grid = sms;
+                CU(c, cudaMalloc(&d.d_solo, rpf_solo65536_scratch_bytes(d.solo_grid)));
+                CU(c, cudaMemset(d.d_solo, 0, rpf_solo65536_scratch_bytes(d.solo_grid)));
+                d.cluster_grid = 0;
+                d.grid = d.solo_grid * 16;                          // private rows: 16 per CTA
             }
             break;
         }
@@ -613,7 +629,7 @@ void rpf_destroy(rpf_ctx *c)
             if (d.ev_consumed[i]) cudaEventDestroy(d.ev_consumed[i]);
         }
         cudaFree(d.d_twiddle); cudaFree(d.d_twiddle_big); cudaFree(d.d_window);
-        cudaFree(d.d_rows); cudaFree(d.d_pwr); cudaFree(d.d_tmp); cudaFree(d.d_baseline); cudaFree(d.d_scratch);
+        cudaFree(d.d_rows); cudaFree(d.d_pwr); cudaFree(d.d_tmp); cudaFree(d.d_baseline); cudaFree(d.d_scratch); cudaFree(d.d_solo);
         cudaFree(d.d_chirp); cudaFree(d.d_bhat); cudaFree(d.d_blue[0]); cudaFree(d.d_blue[1]);
         if (d.own_stream) cudaStreamDestroy(d.own_stream);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
@@ -876,7 +892,7 @@ const char *rpf_plan_name(const rpf_ctx *c)
     if (c->plan == PLAN_BLUESTEIN) return c->blueM == c->N ? "gfft" : "bluestein";
     if (c->plan == PLAN_FUSED3) return c->usepipe ? "pipe4096" : c->use_batched ? "pipe4096_batched" : c->use_pipen ? "pipen" : "fused3";
     if (c->plan == PLAN_FOURSTEP)
-        return !c->devs.empty() && c->devs[0].cluster_grid ? "cluster65536" : c->old_outer ? "fourstep_plain_outer" : "fourstep";
+        return !c->devs.empty() && c->devs[0].solo_grid ? "solo65536" : !c->devs.empty() && c->devs[0].cluster_grid ? "cluster65536" : c->old_outer ? "fourstep_plain_outer" : "fourstep";
     return c->plan == PLAN_SMALL ? "small" : "direct";
 }
 

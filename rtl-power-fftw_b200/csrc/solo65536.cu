@@ -1,0 +1,406 @@
+// solo65536.cu -- N = 65536 in ONE launch, one CTA per spectrum, thread-private hand-off.
+//
+// n = 4096 n1 + m, k = ko + 16 k'.  The two-kernel four-step path writes the outer radix-16 to a complex64 scratch and
+// reads it back (2 + 8 + 8 B of DRAM traffic per sample); the cluster kernel scatters it through distributed shared
+// memory and is bound by that.  This kernel rests on one observation: with m = 256 a + t, the thread that runs the
+// outer radix-16 of column m produces, for every ko, exactly the value that THREAD t ITSELF needs as input a of pass 1
+// of the inner 4096-point transform of outer bin ko.  So if one CTA owns a whole spectrum, the hand-off between the
+// outer pass and the 16 inner transforms is private to each thread:
+//
+//   * the 256 values a thread hands to itself per spectrum go through a per-CTA scratch of 512 KiB in global memory
+//     (148 x 512 KiB = 74 MB: meant to stay in the 126 MB L2).  Thread t only ever touches [..][t]: no barrier, no
+//     fence, no flag -- a thread reads its own writes.  Written with st.global (16 per outer stage, 256 B per warp),
+//     read back with ld.global.cg straight into the registers of the stream that is idle (16 per inner transform,
+//     issued a whole stage before pass 1 needs them: an L2 hit is 260 cycles away); no row slot in shared memory;
+//   * the scratch is reused IN PLACE: spectrum s lives as [ko][a] blocks of 2 KiB, spectrum s + 1 as [a][ko] -- outer
+//     stage a of the next spectrum overwrites exactly the row ko = a of the current one, which was consumed one
+//     iteration earlier (rows 2i, 2i+1 are read at the end of iteration i - 1, stages a = 2i, 2i+1 run in iteration i);
+//   * a CTA that runs all 16 inner transforms needs 16 x 16 accumulators per thread: they live in TENSOR MEMORY used
+//     as a per-thread scratchpad (256 KiB = 256 floats per thread: tcgen05.ld.x16, 32 FFMA, tcgen05.st.x16 per inner
+//     transform), flushed to the CTA's float64 rows every 128 spectra like everywhere else;
+//   * the twiddle W_65536^{(256 a + t) ko} of the outer pass is kept in registers and advanced from a to a + 1 by a
+//     multiplication with the compile-time constant W_256^{ko}, reloaded exactly at a = 0 of every spectrum.
+//
+// Iteration = two inner transforms (streams A: ko = 2i, B: ko = 2i + 1 of the same spectrum) + two outer stages of the
+// next spectrum, 8 iterations per spectrum, stage order (A,1)(B,1)(A,2)(B,2) O O (A,3)(B,3) as in cluster65536.cu; the
+// S1/S2 exchanges and their four split barriers are those of pipe4096.cu.  Raw bytes: 16 bulk copies of 1 KiB per
+// iteration (the 512 columns of both outer stages x 16 values of n1) into a four-deep ring with a full/empty mbarrier
+// pair per slot.  No window (a windowed 65536-bin transform takes the two-kernel path).
+//
+// Replaces reference src/datastore.cxx:68-87 for N = 65536.
+#include <stdint.h>
+#include <type_traits>
+#include "fft_math.cuh"
+#include "rpf_internal.h"
+#include "stage_prims.cuh"
+
+namespace {
+
+constexpr int kN = 4096;                      // inner transform
+constexpr int kM = 16;                        // outer radix
+constexpr int kBig = kN * kM;
+constexpr int kThreads = 256;                 // compute threads (8 warps)
+constexpr int kLaunchThreads = kThreads + 128;
+#ifndef RPF_SOLO_FLUSH
+#define RPF_SOLO_FLUSH 128
+#endif
+constexpr int kFlushSpectra = RPF_SOLO_FLUSH; // float32 partial sums over at most this many spectra
+constexpr int kRowBytes = kN * 8;             // one complex64 row of the inner transform
+constexpr int kBlk = 256 * 8;                 // scratch block: 256 threads x one complex64 = 2 KiB
+constexpr int kPairChunk = 1024;              // raw bytes per n1 and iteration: 2 outer stages x 256 columns x 2 B
+constexpr int kRawSlot = kM * kPairChunk;     // 16 KiB
+#ifndef RPF_SOLO_RAWSTG
+#define RPF_SOLO_RAWSTG 4
+#endif
+constexpr int kRawStg = RPF_SOLO_RAWSTG;      // power of two
+// shared memory: header | S1 [stream] | S2 [stream] | raw ring [slot]
+constexpr int kHdr = 256;
+constexpr int kOffS1 = kHdr;
+constexpr int kOffS2 = kOffS1 + 2 * kRowBytes;
+constexpr int kOffRaw = kOffS2 + 2 * kRowBytes;
+constexpr size_t kSmem = (size_t)kOffRaw + kRawStg * kRawSlot;
+static_assert(kSmem <= 232448, "shared memory per CTA");
+// mbarriers (8 bytes each)
+__device__ __forceinline__ constexpr int bar_rd(int s, int e) { return 2 * s + (e - 1); }        // 0..3: 8 warps
+__device__ __forceinline__ constexpr int bar_full(int slot) { return 4 + slot; }                 // tx 16 KiB
+__device__ __forceinline__ constexpr int bar_empty(int slot) { return 4 + kRawStg + slot; }      // 8 warps
+constexpr int kTmemSlotOff = 8 * (4 + 2 * kRawStg);   // uint32: TMEM base address written by tcgen05.alloc
+static_assert(kTmemSlotOff + 4 <= kHdr && (kRawStg & (kRawStg - 1)) == 0, "header");
+constexpr int kTmemCols = 512;
+
+// W_256^k, k = 0..15 (cos, -sin)
+__host__ __device__ constexpr float w256_re(int k)
+{
+    return k == 0 ? 1.0f : k == 1 ? 0.99969881869620425f : k == 2 ? 0.99879545620517241f : k == 3 ? 0.99729045667869021f
+         : k == 4 ? 0.99518472667219693f : k == 5 ? 0.99247953459870997f : k == 6 ? 0.98917650996478101f
+         : k == 7 ? 0.98527764238894122f : k == 8 ? 0.98078528040323043f : k == 9 ? 0.97570213003852857f
+         : k == 10 ? 0.97003125319454397f : k == 11 ? 0.96377606579543984f : k == 12 ? 0.95694033573220882f
+         : k == 13 ? 0.94952818059303667f : k == 14 ? 0.94154406518302081f : 0.93299279883473896f;
+}
+__host__ __device__ constexpr float w256_im(int k)
+{
+    return k == 0 ? 0.0f : k == 1 ? -0.024541228522912288f : k == 2 ? -0.049067674327418015f : k == 3 ? -0.073564563599667426f
+         : k == 4 ? -0.098017140329560604f : k == 5 ? -0.1224106751992162f : k == 6 ? -0.14673047445536175f
+         : k == 7 ? -0.17096188876030122f : k == 8 ? -0.19509032201612825f : k == 9 ? -0.2191012401568698f
+         : k == 10 ? -0.24298017990326387f : k == 11 ? -0.26671275747489837f : k == 12 ? -0.29028467725446233f
+         : k == 13 ? -0.31368174039889152f : k == 14 ? -0.33688985339222005f : -0.35989503653498811f;
+}
+
+template <int STRIDE>
+__device__ __forceinline__ void lds16x16(uint32_t base, uint32_t (&raw)[16])
+{
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(raw[n1]) : "r"(base + n1 * STRIDE));
+}
+template <int STRIDE>
+__device__ __forceinline__ void lds64x16(uint32_t base, c32 (&v)[16])
+{
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[i].x), "=f"(v[i].y) : "r"(base + i * STRIDE));
+}
+__device__ __forceinline__ void sts_s1(uint32_t base, const c32 (&v)[16])
+{
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base ^ (u << 4)), "f"(v[2 * u].x), "f"(v[2 * u].y),
+                     "f"(v[2 * u + 1].x), "f"(v[2 * u + 1].y) : "memory");
+}
+__device__ __forceinline__ void sts_s2(uint32_t base, const c32 (&v)[16])
+{
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++)
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(base + k2 * 2048), "f"(v[k2].x), "f"(v[k2].y) : "memory");
+}
+__device__ __forceinline__ void warp_arrive(uint32_t bar)
+{
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+// the thread's own 8 bytes of the scratch, from L2
+__device__ __forceinline__ c32 ldg_c32(const void *p)
+{
+    c32 v;
+    asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg_c32(void *p, c32 v)
+{
+    asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// tensor memory as a per-thread scratchpad: 16 consecutive 32-bit columns of the thread's lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+          "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),
+          "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// CTA c takes the spectra c, c + grid, ... of the launch.  scratch: 65536 complex64 per CTA; rows: 16 private rows of
+// 4096 doubles per CTA (row 16 c + ko = outer bin ko, natural order k'), summed by reduce_rows_fourstep().
+__global__ void __launch_bounds__(kLaunchThreads, 1)
+solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__restrict__ twiddle,
+                 const float2 *__restrict__ twbig, float2 *__restrict__ scratch, double *__restrict__ rows)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sm = smem_u32(smem);
+    const int tid = threadIdx.x;
+    const int lo = tid & 15, hi = tid >> 4;       // pass 2: (k1 = lo, n3 = hi); pass 3: (k1 = lo, k2 = hi)
+
+    // ---- work range ------------------------------------------------------------------------
+    const int mine = (int)((nspec - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x);   // >= 1: the host launches no idle CTA
+    if (mine <= 0) return;
+    const int nit = 8 * mine;
+    const int npairs = 8 + nit;                   // raw pair slots consumed: 8 in the prologue, one per iteration
+    auto spectrum_of = [&](int idx) { return (int64_t)blockIdx.x + (int64_t)gridDim.x * min(idx, mine - 1); };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kRawStg; s++) {
+            mbar_init(sm + 8 * bar_full(s), 1);
+            mbar_init(sm + 8 * bar_empty(s), kThreads / 32);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) mbar_init(sm + 8 * i, kThreads / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm + kTmemSlotOff), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(smem + kTmemSlotOff);
+
+    if (tid >= kThreads) {                             // the copy warp group: one lane works
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (tid == kThreads) {
+            for (int p = 0; p < npairs; p++) {
+                const int slot = p & (kRawStg - 1);
+                if (p >= kRawStg) mbar_wait(sm + 8 * bar_empty(slot), (uint32_t)((p / kRawStg - 1) & 1));
+                // pair p: outer stages a = 2 (p & 7), 2 (p & 7) + 1 of my spectrum number p >> 3 (one past the end: re-read)
+                const uint8_t *src = bytes + (size_t)spectrum_of(p >> 3) * (2 * kBig) + (size_t)(p & 7) * kPairChunk;
+                const uint32_t bar = sm + 8 * bar_full(slot), dst = sm + kOffRaw + slot * kRawSlot;
+                mbar_expect_tx(bar, kRawSlot);
+#pragma unroll
+                for (int n1 = 0; n1 < kM; n1++) tma_load_1d(dst + n1 * kPairChunk, src + (size_t)n1 * 2 * kN, kPairChunk, bar);
+            }
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+
+    // ---- per-thread constants ----------------------------------------------------------------
+    float2 tw1[15], tw2[15], twO[15];
+#pragma unroll
+    for (int k = 1; k < 16; k++) {
+        tw1[k - 1] = twiddle[(tid * k) & (kN - 1)];             // W_4096^{t k1}
+        tw2[k - 1] = twiddle[(hi * k * 16) & (kN - 1)];         // W_256^{n3 k2}
+    }
+    auto reload_twO = [&]() {                                    // W_65536^{t ko}: column m = t (a = 0)
+#pragma unroll
+        for (int k = 1; k < 16; k++) twO[k - 1] = twbig[(tid * k) & (kBig - 1)];
+    };
+    reload_twO();
+
+    // my accumulators: lanes of my warp's quadrant, columns [256 (warp >> 2), +256): column 16 ko + k3
+    const uint32_t tm_acc = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) * 256);
+    {
+        float z[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) z[k] = 0.0f;
+#pragma unroll 1
+        for (int ko = 0; ko < 16; ko++) tmem_st16(tm_acc + ko * 16, z);
+        tmem_st_wait();
+    }
+
+    uint8_t *sbase = reinterpret_cast<uint8_t *>(scratch + (size_t)blockIdx.x * kBig + tid);   // my column of every block
+    const uint32_t raw_ld = sm + kOffRaw + 2 * tid;              // + slot * 16 KiB + half * 512 + n1 * 1024
+    const uint32_t s1_st = sm + kOffS1 + tid * 128 + ((tid & 7) << 4);
+    const uint32_t s1_ld = sm + kOffS1 + hi * 128 + ((((lo >> 1) ^ (hi & 7)) << 4) | ((lo & 1) << 3));   // + n2 * 2048
+    const uint32_t s2_st = sm + kOffS2 + hi * 128 + lo * 8;                                              // + k2 * 2048
+    const uint32_t s2_ld = sm + kOffS2 + hi * 2048 + lo * 8;                                             // + n3 * 128
+    constexpr uint32_t kStreamS = kRowBytes;
+
+    double *row = rows + (size_t)blockIdx.x * kBig + tid;        // + ko * 4096 + 256 k3
+    auto flush = [&]() {
+        float z[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) z[k] = 0.0f;
+#pragma unroll 1
+        for (int ko = 0; ko < 16; ko++) {
+            float a16[16];
+            tmem_ld16(tm_acc + ko * 16, a16);
+            double cur[16];
+            double *r = row + ko * kN;
+#pragma unroll
+            for (int k3 = 0; k3 < 16; k3++) cur[k3] = r[256 * k3];
+            tmem_ld_wait();
+#pragma unroll
+            for (int k3 = 0; k3 < 16; k3++) r[256 * k3] = cur[k3] + (double)a16[k3];     // inner bin k' = tid + 256 k3
+            tmem_st16(tm_acc + ko * 16, z);
+        }
+        tmem_st_wait();
+    };
+    c32 vA[16], vB[16];
+    uint32_t raw[16];
+    float acc[16];
+
+    auto post1 = [&](c32 (&v)[16], int s) {
+#pragma unroll
+        for (int k = 1; k < 16; k++) v[k] = cmul(v[k], tw1[k - 1]);
+        sts_s1(s1_st + s * kStreamS, v);
+        warp_arrive(sm + 8 * bar_rd(s, 1));
+    };
+    auto post2 = [&](c32 (&v)[16], int s, auto &&late) {
+#pragma unroll
+        for (int k = 1; k < 16; k++) v[k] = cmul(v[k], tw2[k - 1]);
+        late();
+        sts_s2(s2_st + s * kStreamS, v);
+        warp_arrive(sm + 8 * bar_rd(s, 2));
+    };
+    auto power = [&](const c32 (&v)[16]) {
+#pragma unroll
+        for (int k3 = 0; k3 < 16; k3++) acc[k3] = fmaf(v[k3].x, v[k3].x, fmaf(v[k3].y, v[k3].y, acc[k3]));
+    };
+    auto radix = [&](c32 (&v)[16], auto &&fetch) {
+        c32 y[16];
+        dft16_first(v);
+        dft16_second_a(v, y);
+        dft16_second_b(v, y);
+        fetch();
+    };
+    // raw bytes of pair p, outer stage `half` of it -> raw[]
+    auto fetch_raw = [&](int p, int half) {
+        const int slot = p & (kRawStg - 1);
+        if (half == 0) mbar_wait(sm + 8 * bar_full(slot), (uint32_t)((p / kRawStg) & 1));
+        lds16x16<kPairChunk>(raw_ld + slot * kRawSlot + half * 512, raw);
+    };
+    // Outer stage a of a spectrum stored with parity `par`: raw[] holds x[4096 n1 + 256 a + t].  Radix-16 over n1 on the
+    // biased bytes (exact, as in pass 1 of pipe4096.cu), times W_65536^{(256 a + t) ko}, 16 stores into my column of the
+    // blocks (ko, a); then the twiddles move on to a + 1.
+    auto outer = [&](c32 (&v)[16], int a, int par, auto &&fetch) {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) v[n1] = unpack_biased(raw[n1]);
+        radix(v, fetch);
+        v[0] = __fadd2_rn(v[0], make_float2(-16.0f * kBias, -16.0f * kBias));   // the bias survives in ko = 0 only (exact)
+#pragma unroll
+        for (int k = 1; k < 16; k++) v[k] = cmul(v[k], twO[k - 1]);
+        if (par == 0) {                                          // blocks [ko][a]
+            uint8_t *p = sbase + a * kBlk;
+#pragma unroll
+            for (int ko = 0; ko < 16; ko++) stg_c32(p + ko * (16 * kBlk), v[ko]);
+        } else {                                                 // blocks [a][ko]
+            uint8_t *p = sbase + a * (16 * kBlk);
+#pragma unroll
+            for (int ko = 0; ko < 16; ko++) stg_c32(p + ko * kBlk, v[ko]);
+        }
+#pragma unroll
+        for (int k = 1; k < 16; k++) twO[k - 1] = cmul(twO[k - 1], w256_re(k), w256_im(k));
+    };
+    // my 16 inputs x[256 a + t] of the inner transform ko (spectrum stored with parity `par`) -> registers
+    auto load_row = [&](c32 (&v)[16], int ko, int par) {
+        if (par == 0) {
+            const uint8_t *p = sbase + ko * (16 * kBlk);
+#pragma unroll
+            for (int a = 0; a < 16; a++) v[a] = ldg_c32(p + a * kBlk);
+        } else {
+            const uint8_t *p = sbase + ko * kBlk;
+#pragma unroll
+            for (int a = 0; a < 16; a++) v[a] = ldg_c32(p + a * (16 * kBlk));
+        }
+    };
+
+    // ---- prologue: the whole outer pass of my first spectrum; rows 0 and 1 on their way; row A in registers ------
+    fetch_raw(0, 0);
+#pragma unroll 1
+    for (int pp = 0; pp < 8; pp++) {
+        outer(vB, 2 * pp, 0, [&]() { fetch_raw(pp, 1); });
+        outer(vB, 2 * pp + 1, 0, [&]() {});
+        warp_arrive(sm + 8 * bar_empty(pp & (kRawStg - 1)));
+        if (pp < 7) fetch_raw(pp + 1, 0);
+    }
+    load_row(vA, 0, 0);
+    load_row(vB, 1, 0);
+
+    const uint32_t rd = sm + 8 * bar_rd(0, 1);           // bar_rd(s, e) = rd + 8 (2 s + e - 1)
+    int since_flush = 0;
+    for (int j = 0; j < nit; j++) {
+        const uint32_t ph = (uint32_t)(j & 1);
+        const int i = j & 7;                              // streams A, B = outer bins 2i, 2i + 1 of spectrum j >> 3
+        const int par = (j >> 3) & 1;
+        if (i == 0) reload_twO();                         // the outer stages of this spectrum's successor start at a = 0
+
+        // ---- (A,1) --------------------------------------------------------------------------------
+        radix(vA, []() {});
+        post1(vA, 0);
+        // ---- (B,1) | S1[A] ------------------------------------------------------------------------
+        radix(vB, [&]() { mbar_wait(rd, ph); lds64x16<2048>(s1_ld, vA); });
+        post1(vB, 1);
+        // ---- (A,2) | S1[B] ------------------------------------------------------------------------
+        radix(vA, [&]() { mbar_wait(rd + 16, ph); lds64x16<2048>(s1_ld + kStreamS, vB); });
+        post2(vA, 0, []() {});
+        // ---- (B,2) | S2[A]; raw bytes of the first outer stage ---------------------------------------
+        radix(vB, [&]() { mbar_wait(rd + 8, ph); lds64x16<128>(s2_ld, vA); });
+        post2(vB, 1, [&]() { fetch_raw(8 + j, 0); });
+        // ---- O(2i), O(2i + 1) of the next spectrum (parity par ^ 1) ---------------------------------
+        outer(vB, 2 * i, par ^ 1, [&]() { fetch_raw(8 + j, 1); });
+        outer(vB, 2 * i + 1, par ^ 1, [&]() {});
+        warp_arrive(sm + 8 * bar_empty(j & (kRawStg - 1)));
+        // the rows of the next iteration: ko = 2i + 2, 2i + 3 of this spectrum, or 0, 1 of the next one
+        const int kon = (2 * i + 2) & 15, parn = par ^ (i == 7 ? 1 : 0);
+        // ---- (A,3) | S2[B] ------------------------------------------------------------------------
+        tmem_st_wait();                                   // (the stores of the previous iteration: long done)
+        tmem_ld16(tm_acc + (2 * i) * 16, acc);
+        radix(vA, [&]() { mbar_wait(rd + 24, ph); lds64x16<128>(s2_ld + kStreamS, vB); });
+        tmem_ld_wait();
+        power(vA);
+        tmem_st16(tm_acc + (2 * i) * 16, acc);
+        load_row(vA, kon, parn);                          // lands under (B,3)
+        // ---- (B,3) ----------------------------------------------------------------------------------
+        tmem_ld16(tm_acc + (2 * i + 1) * 16, acc);
+        radix(vB, []() {});
+        tmem_ld_wait();
+        power(vB);
+        tmem_st16(tm_acc + (2 * i + 1) * 16, acc);
+        load_row(vB, kon + 1, parn);                      // lands under (A,1) of the next iteration
+
+        if (i == 7 && ++since_flush == kFlushSpectra) { tmem_st_wait(); flush(); since_flush = 0; }
+    }
+    tmem_st_wait();
+    flush();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+}  // namespace
+
+cudaError_t rpf_solo65536_configure()
+{
+    return cudaFuncSetAttribute(solo65536_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+}
+
+size_t rpf_solo65536_scratch_bytes(int grid) { return (size_t)grid * kBig * sizeof(float2); }
+
+// L.grid = CTAs (<= SMs), L.rows = 16 rows of 4096 doubles per CTA, scratch = rpf_solo65536_scratch_bytes(L.grid).
+cudaError_t rpf_launch_solo65536(const RpfLaunch &L, const float2 *twbig, float2 *scratch)
+{
+    if (L.nspec <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((int64_t)L.grid < L.nspec ? L.grid : L.nspec);
+    solo65536_kernel<<<grid, kLaunchThreads, kSmem, L.stream>>>(L.bytes, L.nspec, L.twiddle, twbig, scratch, L.rows);
+    return cudaGetLastError();
+}

@@ -525,6 +525,63 @@ def test_cluster65536_matches_two_kernel_path_and_oracle(R):
     assert pc.sum() == pytest.approx(N * float((x * x).sum()), rel=1e-6)
 
 
+@pytest.mark.parametrize("R", [1, 2, 3, 7, 9, 147, 148, 149, 297, 600, 1500])
+def test_solo65536_matches_two_kernel_path_and_oracle(R):
+    """RPF_FLAG_SOLO65536: 65536 bins in one launch, one CTA per spectrum (csrc/solo65536.cu): the outer radix-16 handed
+    to the 16 inner transforms thread-privately through an in-place scratch whose layout alternates between [ko][a] and
+    [a][ko], accumulators in tensor memory.  Spectrum counts below, at and above the CTA count (one, two, three ... and
+    unequal numbers of spectra per CTA, i.e. both layouts and the re-read of the last spectrum): against the two-kernel
+    four-step path, the oracle for small counts, Parseval."""
+    N = 65536
+    s = stream(2 * N * R, seed=R * 17 + 3, mode=1)
+    with Context(N, flags=pkg.capi.RPF_FLAG_SOLO65536) as c:
+        assert c.plan_name == "solo65536"
+    ps, done = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_SOLO65536)
+    pt, done_t = run_gpu(N, R, [s])
+    assert done == done_t == R
+    assert relmax(ps, pt) < 2e-6 and perbin(ps, pt) < 2e-5
+    if R <= 9:
+        po, _ = ol.oracle_run_stream(N, R, s, buf_length=s.size)
+        assert relmax(ps, po) < TOL
+        assert perbin(ps, po) < (TOL if R >= 9 else 1e-3)
+    x = s.astype(np.int64) - 127
+    assert ps.sum() == pytest.approx(N * float((x * x).sum()), rel=1e-6)
+
+
+def test_solo65536_kats_pushes_and_reuse():
+    """The one-CTA-per-spectrum kernel on known answers (zero input, DC, a tone: bin exact), over several pushes that
+    straddle spectra, and reused after rpf_reset (tensor-memory accumulators and float64 rows start from zero)."""
+    N, F = 65536, pkg.capi.RPF_FLAG_SOLO65536
+    with Context(N, flags=F) as c:
+        z = np.full(2 * N * 3, 127, dtype=np.uint8)
+        c.reset(3); c.push(z); p, done = c.finish()
+        assert done == 3 and np.all(p == 0.0)
+        d = np.full(2 * N * 2, 127, dtype=np.uint8); d[0::2] = 137
+        c.reset(2); c.push(d); p, done = c.finish()
+        assert done == 2 and int(np.argmax(p)) == N // 2 and p[N // 2] == pytest.approx(2 * (10.0 * N) ** 2, rel=1e-6)
+        assert np.all(np.delete(p, N // 2) <= 1e-6 * p[N // 2])
+        k0 = 12345
+        n = np.arange(N)
+        t = np.empty(2 * N, dtype=np.uint8)
+        t[0::2] = np.round(127 + 100 * np.cos(2 * np.pi * k0 * n / N)).astype(np.uint8)
+        t[1::2] = np.round(127 + 100 * np.sin(2 * np.pi * k0 * n / N)).astype(np.uint8)
+        c.reset(1); c.push(t); p, done = c.finish()
+        assert done == 1 and int(np.argmax(p)) == (k0 + N // 2) % N
+        R = 301
+        s = stream(2 * N * R, seed=99, mode=1)
+        cuts = [0, 1000, 2 * N + 6, 2 * N * 150 + 2, 2 * N * 150 + 4, s.size]
+        c.reset(R)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            c.push(s[a:b])
+        p1, done = c.finish()
+        assert done == R
+        c.reset(R); c.push(s); p2, done = c.finish()
+        assert done == R
+    pt, _ = run_gpu(N, R, [s])
+    assert relmax(p1, pt) < 2e-6 and perbin(p1, pt) < 2e-5
+    assert relmax(p1, p2) < 1e-6
+
+
 @pytest.mark.parametrize("N,R", [(8192, 37), (16384, 300), (32768, 5), (65536, 1), (65536, 19), (65536, 700)])
 @pytest.mark.parametrize("windowed", [False, True])
 def test_tma_outer_pass_is_bit_identical_to_the_plain_one(N, R, windowed):
