@@ -99,7 +99,7 @@ typedef struct rpf_config {
  * handed to the inner 4096-point pipelines through distributed shared memory (st.async + remote mbarriers) instead of
  * a complex64 scratch in HBM.  Same results; measured slower than the default two-kernel path. */
 #define RPF_FLAG_CLUSTER65536 16u
-/* N = 65536 without a window: the whole transform in one launch, one CTA per spectrum; the outer radix-16 is handed to
+/* N = 65536: the whole transform in one launch, one CTA per spectrum; the outer radix-16 is handed to
  * the 16 inner 4096-point transforms thread-privately through a 512 KiB per-CTA scratch that stays in L2, the 65536
  * accumulators of a CTA live in tensor memory (csrc/solo65536.cu).  Same results. */
 #define RPF_FLAG_SOLO65536 64u

@@ -401,9 +401,11 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
                 d.cluster_grid = ncl * 16;
             }
             // RPF_FLAG_SOLO65536 (65536 bins, no window): one launch, one CTA per spectrum (solo65536.cu)
-            if (c->M == 16 && !cfg->window && (cfg->flags & RPF_FLAG_SOLO65536)) {
+            if (c->M == 16 && (cfg->flags & RPF_FLAG_SOLO65536)) {
                 CU(c, rpf_solo65536_configure());
                 d.solo_grid = sms;
+                // rpf_config.scratch_mib bounds the scratch (512 KiB per CTA) and with it the CTA count (tuning runs)
+                if (cfg->scratch_mib > 0 && cfg->scratch_mib * 2 < d.solo_grid) d.solo_grid = cfg->scratch_mib * 2;
                 CU(c, cudaMalloc(&d.d_solo, rpf_solo65536_scratch_bytes(d.solo_grid)));
                 CU(c, cudaMemset(d.d_solo, 0, rpf_solo65536_scratch_bytes(d.solo_grid)));
                 d.cluster_grid = 0;

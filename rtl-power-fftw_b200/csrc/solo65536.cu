@@ -25,10 +25,12 @@
 // next spectrum, 8 iterations per spectrum, stage order (A,1)(B,1)(A,2)(B,2) O O (A,3)(B,3) as in cluster65536.cu; the
 // S1/S2 exchanges and their four split barriers are those of pipe4096.cu.  Raw bytes: 16 bulk copies of 1 KiB per
 // iteration (the 512 columns of both outer stages x 16 values of n1) into a four-deep ring with a full/empty mbarrier
-// pair per slot.  No window (a windowed 65536-bin transform takes the two-kernel path).
+// pair per slot.  With a window: byte - 127 (exact), the 16 window values of an outer stage come from global memory (L2)
+// and ride in the first radix-4 layer of the outer radix-16 (dft16_first_windowed), as in pipe4096.cu.
 //
 // Replaces reference src/datastore.cxx:68-87 for N = 65536.
 #include <stdint.h>
+#include <stdio.h>
 #include <type_traits>
 #include "fft_math.cuh"
 #include "rpf_internal.h"
@@ -50,7 +52,7 @@ constexpr int kBlk = 256 * 8;                 // scratch block: 256 threads x on
 constexpr int kPairChunk = 1024;              // raw bytes per n1 and iteration: 2 outer stages x 256 columns x 2 B
 constexpr int kRawSlot = kM * kPairChunk;     // 16 KiB
 #ifndef RPF_SOLO_RAWSTG
-#define RPF_SOLO_RAWSTG 4
+#define RPF_SOLO_RAWSTG 2
 #endif
 constexpr int kRawStg = RPF_SOLO_RAWSTG;      // power of two
 // shared memory: header | S1 [stream] | S2 [stream] | raw ring [slot]
@@ -124,9 +126,41 @@ __device__ __forceinline__ c32 ldg_c32(const void *p)
     asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ c32 ldg_c32_hint(const void *p, uint64_t pol)
+{
+    c32 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+// RPF_SOLO_HINTS = 1: L2 eviction priorities -- the raw stream is read once (evict_first), the scratch is what should
+// stay (evict_last on its stores and loads)
+#ifndef RPF_SOLO_HINTS
+#define RPF_SOLO_HINTS 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void stg_c32(void *p, c32 v)
 {
     asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_c32_hint(void *p, c32 v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
 }
 
 // tensor memory as a per-thread scratchpad: 16 consecutive 32-bit columns of the thread's lane
@@ -150,9 +184,11 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // CTA c takes the spectra c, c + grid, ... of the launch.  scratch: 65536 complex64 per CTA; rows: 16 private rows of
 // 4096 doubles per CTA (row 16 c + ko = outer bin ko, natural order k'), summed by reduce_rows_fourstep().
+template <bool WINDOW>
 __global__ void __launch_bounds__(kLaunchThreads, 1)
 solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__restrict__ twiddle,
-                 const float2 *__restrict__ twbig, float2 *__restrict__ scratch, double *__restrict__ rows)
+                 const float2 *__restrict__ twbig, const float *__restrict__ window, float2 *__restrict__ scratch,
+                 double *__restrict__ rows)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sm = smem_u32(smem);
@@ -188,6 +224,9 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
     if (tid >= kThreads) {                             // the copy warp group: one lane works
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (tid == kThreads) {
+#if RPF_SOLO_HINTS
+            const uint64_t pol_raw = l2_policy_evict_first();
+#endif
             for (int p = 0; p < npairs; p++) {
                 const int slot = p & (kRawStg - 1);
                 if (p >= kRawStg) mbar_wait(sm + 8 * bar_empty(slot), (uint32_t)((p / kRawStg - 1) & 1));
@@ -196,7 +235,13 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
                 const uint32_t bar = sm + 8 * bar_full(slot), dst = sm + kOffRaw + slot * kRawSlot;
                 mbar_expect_tx(bar, kRawSlot);
 #pragma unroll
-                for (int n1 = 0; n1 < kM; n1++) tma_load_1d(dst + n1 * kPairChunk, src + (size_t)n1 * 2 * kN, kPairChunk, bar);
+                for (int n1 = 0; n1 < kM; n1++) {
+#if RPF_SOLO_HINTS
+                    tma_load_1d_hint(dst + n1 * kPairChunk, src + (size_t)n1 * 2 * kN, kPairChunk, bar, pol_raw);
+#else
+                    tma_load_1d(dst + n1 * kPairChunk, src + (size_t)n1 * 2 * kN, kPairChunk, bar);
+#endif
+                }
             }
         }
         return;
@@ -227,6 +272,14 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         tmem_st_wait();
     }
 
+#if RPF_SOLO_HINTS
+    const uint64_t pol_keep = l2_policy_evict_last();
+#define RPF_SOLO_STG(p, v) stg_c32_hint((p), (v), pol_keep)
+#define RPF_SOLO_LDG(p) ldg_c32_hint((p), pol_keep)
+#else
+#define RPF_SOLO_STG(p, v) stg_c32((p), (v))
+#define RPF_SOLO_LDG(p) ldg_c32((p))
+#endif
     uint8_t *sbase = reinterpret_cast<uint8_t *>(scratch + (size_t)blockIdx.x * kBig + tid);   // my column of every block
     const uint32_t raw_ld = sm + kOffRaw + 2 * tid;              // + slot * 16 KiB + half * 512 + n1 * 1024
     const uint32_t s1_st = sm + kOffS1 + tid * 128 + ((tid & 7) << 4);
@@ -247,10 +300,10 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
             double cur[16];
             double *r = row + ko * kN;
 #pragma unroll
-            for (int k3 = 0; k3 < 16; k3++) cur[k3] = r[256 * k3];
+            for (int k3 = 0; k3 < 16; k3++) cur[k3] = __ldcs(r + 256 * k3);             // streaming: the rows must not displace the scratch in L2
             tmem_ld_wait();
 #pragma unroll
-            for (int k3 = 0; k3 < 16; k3++) r[256 * k3] = cur[k3] + (double)a16[k3];     // inner bin k' = tid + 256 k3
+            for (int k3 = 0; k3 < 16; k3++) __stcs(r + 256 * k3, cur[k3] + (double)a16[k3]);   // inner bin k' = tid + 256 k3
             tmem_st16(tm_acc + ko * 16, z);
         }
         tmem_st_wait();
@@ -283,6 +336,13 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         dft16_second_b(v, y);
         fetch();
     };
+    float win[WINDOW ? 16 : 1];
+    auto load_window = [&](int a) {                  // w[4096 n1 + 256 a + t]
+        if (WINDOW) {
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) win[n1] = __ldg(window + n1 * kN + a * 256 + tid);
+        }
+    };
     // raw bytes of pair p, outer stage `half` of it -> raw[]
     auto fetch_raw = [&](int p, int half) {
         const int slot = p & (kRawStg - 1);
@@ -294,19 +354,31 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
     // blocks (ko, a); then the twiddles move on to a + 1.
     auto outer = [&](c32 (&v)[16], int a, int par, auto &&fetch) {
 #pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) v[n1] = unpack_biased(raw[n1]);
-        radix(v, fetch);
-        v[0] = __fadd2_rn(v[0], make_float2(-16.0f * kBias, -16.0f * kBias));   // the bias survives in ko = 0 only (exact)
+        for (int n1 = 0; n1 < 16; n1++) {
+            v[n1] = unpack_biased(raw[n1]);
+            if (WINDOW) v[n1] = __fadd2_rn(v[n1], make_float2(-kBias, -kBias));   // byte - 127.0f, exact
+        }
+        if (WINDOW) {
+            c32 y[16];
+            dft16_first_windowed(v, win);
+            dft16_second_a(v, y);
+            dft16_second_b(v, y);
+            fetch();
+            load_window((a + 1) & 15);                                           // for the next outer stage
+        } else {
+            radix(v, fetch);
+            v[0] = __fadd2_rn(v[0], make_float2(-16.0f * kBias, -16.0f * kBias));   // the bias survives in ko = 0 only (exact)
+        }
 #pragma unroll
         for (int k = 1; k < 16; k++) v[k] = cmul(v[k], twO[k - 1]);
         if (par == 0) {                                          // blocks [ko][a]
             uint8_t *p = sbase + a * kBlk;
 #pragma unroll
-            for (int ko = 0; ko < 16; ko++) stg_c32(p + ko * (16 * kBlk), v[ko]);
+            for (int ko = 0; ko < 16; ko++) RPF_SOLO_STG(p + ko * (16 * kBlk), v[ko]);
         } else {                                                 // blocks [a][ko]
             uint8_t *p = sbase + a * (16 * kBlk);
 #pragma unroll
-            for (int ko = 0; ko < 16; ko++) stg_c32(p + ko * kBlk, v[ko]);
+            for (int ko = 0; ko < 16; ko++) RPF_SOLO_STG(p + ko * kBlk, v[ko]);
         }
 #pragma unroll
         for (int k = 1; k < 16; k++) twO[k - 1] = cmul(twO[k - 1], w256_re(k), w256_im(k));
@@ -316,15 +388,16 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         if (par == 0) {
             const uint8_t *p = sbase + ko * (16 * kBlk);
 #pragma unroll
-            for (int a = 0; a < 16; a++) v[a] = ldg_c32(p + a * kBlk);
+            for (int a = 0; a < 16; a++) v[a] = RPF_SOLO_LDG(p + a * kBlk);
         } else {
             const uint8_t *p = sbase + ko * kBlk;
 #pragma unroll
-            for (int a = 0; a < 16; a++) v[a] = ldg_c32(p + a * (16 * kBlk));
+            for (int a = 0; a < 16; a++) v[a] = RPF_SOLO_LDG(p + a * (16 * kBlk));
         }
     };
 
-    // ---- prologue: the whole outer pass of my first spectrum; rows 0 and 1 on their way; row A in registers ------
+    // ---- prologue: the whole outer pass of my first spectrum; rows 0 and 1 on their way ------------------------
+    load_window(0);
     fetch_raw(0, 0);
 #pragma unroll 1
     for (int pp = 0; pp < 8; pp++) {
@@ -342,7 +415,7 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         const uint32_t ph = (uint32_t)(j & 1);
         const int i = j & 7;                              // streams A, B = outer bins 2i, 2i + 1 of spectrum j >> 3
         const int par = (j >> 3) & 1;
-        if (i == 0) reload_twO();                         // the outer stages of this spectrum's successor start at a = 0
+        if (i == 0) { reload_twO(); load_window(0); }     // the outer stages of this spectrum's successor start at a = 0
 
         // ---- (A,1) --------------------------------------------------------------------------------
         radix(vA, []() {});
@@ -389,9 +462,23 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
 
 }  // namespace
 
+#ifndef RPF_SOLO_PERSIST
+#define RPF_SOLO_PERSIST 0
+#endif
 cudaError_t rpf_solo65536_configure()
 {
-    return cudaFuncSetAttribute(solo65536_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+#if RPF_SOLO_PERSIST
+    {   // L2 set-aside for persisting (evict_last) lines: as much as the device allows
+        int dev = 0, maxp = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp);
+        fprintf(stderr, "solo65536: persisting L2 set-aside %d MiB\n", maxp >> 20);
+    }
+#endif
+    cudaError_t e = cudaFuncSetAttribute(solo65536_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(solo65536_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
 }
 
 size_t rpf_solo65536_scratch_bytes(int grid) { return (size_t)grid * kBig * sizeof(float2); }
@@ -401,6 +488,9 @@ cudaError_t rpf_launch_solo65536(const RpfLaunch &L, const float2 *twbig, float2
 {
     if (L.nspec <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((int64_t)L.grid < L.nspec ? L.grid : L.nspec);
-    solo65536_kernel<<<grid, kLaunchThreads, kSmem, L.stream>>>(L.bytes, L.nspec, L.twiddle, twbig, scratch, L.rows);
+    if (L.window)
+        solo65536_kernel<true><<<grid, kLaunchThreads, kSmem, L.stream>>>(L.bytes, L.nspec, L.twiddle, twbig, L.window, scratch, L.rows);
+    else
+        solo65536_kernel<false><<<grid, kLaunchThreads, kSmem, L.stream>>>(L.bytes, L.nspec, L.twiddle, twbig, nullptr, scratch, L.rows);
     return cudaGetLastError();
 }

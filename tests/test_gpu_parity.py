@@ -539,13 +539,30 @@ def test_solo65536_matches_two_kernel_path_and_oracle(R):
     ps, done = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_SOLO65536)
     pt, done_t = run_gpu(N, R, [s])
     assert done == done_t == R
-    assert relmax(ps, pt) < 2e-6 and perbin(ps, pt) < 2e-5
+    # (per bin: with a handful of spectra some bins are orders of magnitude below the mean)
+    assert relmax(ps, pt) < 2e-6 and perbin(ps, pt) < (2e-5 if R >= 9 else 1e-3)
     if R <= 9:
         po, _ = ol.oracle_run_stream(N, R, s, buf_length=s.size)
         assert relmax(ps, po) < TOL
         assert perbin(ps, po) < (TOL if R >= 9 else 1e-3)
     x = s.astype(np.int64) - 127
     assert ps.sum() == pytest.approx(N * float((x * x).sum()), rel=1e-6)
+
+
+@pytest.mark.parametrize("R", [3, 149, 300])
+def test_solo65536_window(R):
+    """The same kernel with a Hann window (multiplication fused into the first radix-4 layer of the outer radix-16)."""
+    N = 65536
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32)
+    s = stream(2 * N * R, seed=R + 71, mode=1)
+    ps, done = run_gpu(N, R, [s], window=w, flags=pkg.capi.RPF_FLAG_SOLO65536)
+    pt, done_t = run_gpu(N, R, [s], window=w)
+    assert done == done_t == R
+    # (per bin: with a handful of spectra some bins are orders of magnitude below the mean)
+    assert relmax(ps, pt) < 2e-6 and perbin(ps, pt) < (2e-5 if R >= 9 else 1e-3)
+    if R <= 3:
+        po, _ = ol.oracle_run_stream(N, R, s, window=w, buf_length=s.size)
+        assert relmax(ps, po) < TOL
 
 
 def test_solo65536_kats_pushes_and_reuse():

@@ -5,7 +5,8 @@ mkdir -p gpurun_out
 echo "== solo tests"; timeout -s KILL 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "solo65536" 2>&1 | tail -15
 echo "== kbench 65536 solo"; timeout -s KILL 90 python tools/kbench.py --n 65536 --mb 4096 --reps 5 --flags 64
 echo "== kbench 65536 default"; timeout -s KILL 90 python tools/kbench.py --n 65536 --mb 4096 --reps 5
-for v in rawstg2 flush32; do
+for g in 37 50 60 66; do echo "== kbench 65536 solo, scratch $g MiB = $((2*g)) CTAs"; timeout -s KILL 90 python tools/kbench.py --n 65536 --mb 4096 --reps 3 --flags 64 --scratch-mib $g --no-check; done
+for v in rawstg2 flush32 hints; do
   [ -f variants/librpf_$v.so ] && { echo "== kbench 65536 solo $v"; timeout -s KILL 90 python tools/kbench.py --n 65536 --mb 4096 --reps 5 --flags 64 --lib variants/librpf_$v.so; }
 done
 echo "== ncu traffic solo"
