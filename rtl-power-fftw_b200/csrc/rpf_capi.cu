@@ -93,6 +93,7 @@ struct rpf_dev {
     int cluster_grid = 0;             // N = 65536: CTAs of the resident 16-CTA clusters (0: two-kernel four-step path)
     int solo_grid = 0;                // N = 65536: CTAs of the one-CTA-per-spectrum kernel (0: not selected)
     float2 *d_solo = nullptr;         // ... and their private scratch, 512 KiB each
+    size_t solo_saved_l2 = (size_t)-1;   // the device's persisting-L2 limit before this context raised it
     int rows_dirty = 0;               // private accumulator rows written since the last reset
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[kNumStage] = {}, ev_consumed[kNumStage] = {};
@@ -238,7 +239,9 @@ int rows_touched(const rpf_ctx *c, const rpf_dev &d, int64_t nspec)
             blocks = c->usepipe ? (nspec + 1) / 2 : (nspec + c->groups - 1) / c->groups;
             if (c->use_pipen || c->use_batched) blocks = (blocks + 1) / 2;   // pairs of group iterations / ring slots
             break;
-        case PLAN_FOURSTEP: return d.nrows;
+        case PLAN_FOURSTEP:
+            if (d.solo_grid) return (int)(nspec < d.solo_grid ? nspec : d.solo_grid) * 16;   // 16 rows per CTA that ran
+            return d.nrows;
         case PLAN_BLUESTEIN: return d.nrows;
         default: blocks = nspec;
     }
@@ -402,7 +405,7 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
             }
             // RPF_FLAG_SOLO65536 (65536 bins, no window): one launch, one CTA per spectrum (solo65536.cu)
             if (c->M == 16 && (cfg->flags & RPF_FLAG_SOLO65536)) {
-                CU(c, rpf_solo65536_configure());
+                CU(c, rpf_solo65536_configure(&d.solo_saved_l2));
                 d.solo_grid = sms;
                 // rpf_config.scratch_mib bounds the scratch (512 KiB per CTA) and with it the CTA count (tuning runs)
                 if (cfg->scratch_mib > 0 && cfg->scratch_mib * 2 < d.solo_grid) d.solo_grid = cfg->scratch_mib * 2;
@@ -632,6 +635,7 @@ void rpf_destroy(rpf_ctx *c)
         }
         cudaFree(d.d_twiddle); cudaFree(d.d_twiddle_big); cudaFree(d.d_window);
         cudaFree(d.d_rows); cudaFree(d.d_pwr); cudaFree(d.d_tmp); cudaFree(d.d_baseline); cudaFree(d.d_scratch); cudaFree(d.d_solo);
+        if (d.solo_grid) rpf_solo65536_release(d.solo_saved_l2);
         cudaFree(d.d_chirp); cudaFree(d.d_bhat); cudaFree(d.d_blue[0]); cudaFree(d.d_blue[1]);
         if (d.own_stream) cudaStreamDestroy(d.own_stream);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);

@@ -9,9 +9,11 @@
 //
 //   * the 256 values a thread hands to itself per spectrum go through a per-CTA scratch of 512 KiB in global memory
 //     (148 x 512 KiB = 74 MB: meant to stay in the 126 MB L2).  Thread t only ever touches [..][t]: no barrier, no
-//     fence, no flag -- a thread reads its own writes.  Written with st.global (16 per outer stage, 256 B per warp),
-//     read back with ld.global.cg straight into the registers of the stream that is idle (16 per inner transform,
-//     issued a whole stage before pass 1 needs them: an L2 hit is 260 cycles away); no row slot in shared memory;
+//     fence, no flag on the compute warps' side beyond one mbarrier arrive per iteration.  Written with st.global (16
+//     per outer stage, 256 B per warp); read back by the three otherwise idle warps of the copy warp group with 16-byte
+//     cp.async (LDGSTS) into a 32 KiB row slot per stream, two to three stages before pass 1 needs the row (a first
+//     version loaded the rows with ld.global straight into the idle stream's registers: one stage of distance is less
+//     than the L2 latency under load, 10 % of all warp samples sat on the first use);
 //   * the scratch is reused IN PLACE: spectrum s lives as [ko][a] blocks of 2 KiB, spectrum s + 1 as [a][ko] -- outer
 //     stage a of the next spectrum overwrites exactly the row ko = a of the current one, which was consumed one
 //     iteration earlier (rows 2i, 2i+1 are read at the end of iteration i - 1, stages a = 2i, 2i+1 run in iteration i);
@@ -30,7 +32,6 @@
 //
 // Replaces reference src/datastore.cxx:68-87 for N = 65536.
 #include <stdint.h>
-#include <stdio.h>
 #include <type_traits>
 #include "fft_math.cuh"
 #include "rpf_internal.h"
@@ -55,10 +56,12 @@ constexpr int kRawSlot = kM * kPairChunk;     // 16 KiB
 #define RPF_SOLO_RAWSTG 2
 #endif
 constexpr int kRawStg = RPF_SOLO_RAWSTG;      // power of two
-// shared memory: header | S1 [stream] | S2 [stream] | raw ring [slot]
+// shared memory: header | row slots [stream] | S1 [stream] | S2 [stream] | raw ring [slot]
 constexpr int kHdr = 256;
-constexpr int kOffS1 = kHdr;
+constexpr int kOffRow = kHdr;
+constexpr int kOffS1 = kOffRow + 2 * kRowBytes;
 constexpr int kOffS2 = kOffS1 + 2 * kRowBytes;
+constexpr int kHelpers = 64;                  // warps 9, 10 stage the rows; lane 0 of warp 8 issues the raw bulk copies
 constexpr int kOffRaw = kOffS2 + 2 * kRowBytes;
 constexpr size_t kSmem = (size_t)kOffRaw + kRawStg * kRawSlot;
 static_assert(kSmem <= 232448, "shared memory per CTA");
@@ -66,7 +69,10 @@ static_assert(kSmem <= 232448, "shared memory per CTA");
 __device__ __forceinline__ constexpr int bar_rd(int s, int e) { return 2 * s + (e - 1); }        // 0..3: 8 warps
 __device__ __forceinline__ constexpr int bar_full(int slot) { return 4 + slot; }                 // tx 16 KiB
 __device__ __forceinline__ constexpr int bar_empty(int slot) { return 4 + kRawStg + slot; }      // 8 warps
-constexpr int kTmemSlotOff = 8 * (4 + 2 * kRawStg);   // uint32: TMEM base address written by tcgen05.alloc
+constexpr int kBarWritten = 4 + 2 * kRawStg;          // 8 warps: the whole outer pass of a spectrum is stored
+__device__ __forceinline__ constexpr int bar_rowfull(int s) { return kBarWritten + 1 + s; }     // kHelpers cp.async arrivals
+__device__ __forceinline__ constexpr int bar_rowfree(int s) { return kBarWritten + 3 + s; }     // 8 warps: row slot s has been read
+constexpr int kTmemSlotOff = 8 * (kBarWritten + 5);   // uint32: TMEM base address written by tcgen05.alloc
 static_assert(kTmemSlotOff + 4 <= kHdr && (kRawStg & (kRawStg - 1)) == 0, "header");
 constexpr int kTmemCols = 512;
 
@@ -87,6 +93,13 @@ __host__ __device__ constexpr float w256_im(int k)
          : k == 10 ? -0.24298017990326387f : k == 11 ? -0.26671275747489837f : k == 12 ? -0.29028467725446233f
          : k == 13 ? -0.31368174039889152f : k == 14 ? -0.33688985339222005f : -0.35989503653498811f;
 }
+
+// RPF_SOLO_HINTS = 1: L2 eviction priorities -- the raw stream is read once (evict_first), the scratch is what should
+// stay (evict_last on its stores and loads).  Measured (B200, 4 GiB stream): without 310, with 344 Gsamples/s; DRAM
+// traffic 4.8 x -> 2.1 x the algorithmic 2 B/sample, 1.16 x with the persisting set-aside below.
+#ifndef RPF_SOLO_HINTS
+#define RPF_SOLO_HINTS 1
+#endif
 
 template <int STRIDE>
 __device__ __forceinline__ void lds16x16(uint32_t base, uint32_t (&raw)[16])
@@ -119,24 +132,7 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar)
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
-// the thread's own 8 bytes of the scratch, from L2
-__device__ __forceinline__ c32 ldg_c32(const void *p)
-{
-    c32 v;
-    asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ c32 ldg_c32_hint(const void *p, uint64_t pol)
-{
-    c32 v;
-    asm volatile("ld.global.cg.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol) : "memory");
-    return v;
-}
-// RPF_SOLO_HINTS = 1: L2 eviction priorities -- the raw stream is read once (evict_first), the scratch is what should
-// stay (evict_last on its stores and loads)
-#ifndef RPF_SOLO_HINTS
-#define RPF_SOLO_HINTS 0
-#endif
+#if RPF_SOLO_HINTS
 __device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
     uint64_t p;
@@ -154,14 +150,24 @@ __device__ __forceinline__ void tma_load_1d_hint(uint32_t dst, const void *src, 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void stg_c32(void *p, c32 v)
+__device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void *src, uint64_t pol)
 {
-    asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void stg_c32_hint(void *p, c32 v, uint64_t pol)
 {
     asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
 }
+#else
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void stg_c32(void *p, c32 v)
+{
+    asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+#endif
 
 // tensor memory as a per-thread scratchpad: 16 consecutive 32-bit columns of the thread's lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16])
@@ -210,6 +216,11 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) mbar_init(sm + 8 * i, kThreads / 32);
+        mbar_init(sm + 8 * kBarWritten, kThreads / 32);
+        mbar_init(sm + 8 * bar_rowfull(0), kHelpers);
+        mbar_init(sm + 8 * bar_rowfull(1), kHelpers);
+        mbar_init(sm + 8 * bar_rowfree(0), kThreads / 32);
+        mbar_init(sm + 8 * bar_rowfree(1), kThreads / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 32) {
@@ -221,8 +232,47 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *reinterpret_cast<const volatile uint32_t *>(smem + kTmemSlotOff);
 
-    if (tid >= kThreads) {                             // the copy warp group: one lane works
+    if (tid >= kThreads) {                             // the copy warp group
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (tid >= kThreads + 32 && tid < kThreads + 32 + kHelpers) {
+            // Row staging: generation g = the rows ko = 2i, 2i + 1 (i = g & 7) of my spectrum number g >> 3, wanted by
+            // iteration g.  A row is fetched as soon as its slot has been read for generation g - 1 (a whole iteration
+            // before it is needed); only the first two rows of a spectrum also have to wait for the last outer stages of
+            // that spectrum (`written`, once per spectrum), which leaves them two to three stages.
+            const int h = tid - (kThreads + 32);
+            const uint8_t *cta_scratch = reinterpret_cast<const uint8_t *>(scratch + (size_t)blockIdx.x * kBig);
+#if RPF_SOLO_HINTS
+            const uint64_t pol_rows = l2_policy_evict_last();
+#endif
+            for (int g = 0; g <= nit; g++) {       // (generation nit is never transformed: the loop stays branch-free)
+                const int par = (g >> 3) & 1;
+#pragma unroll 1
+                for (int s = 0; s < 2; s++) {
+                    if (g > 0) mbar_wait_parked(sm + 8 * bar_rowfree(s), (uint32_t)((g - 1) & 1), 1000);
+                    if (s == 0 && (g & 7) == 0) mbar_wait_parked(sm + 8 * kBarWritten, (uint32_t)((g >> 3) & 1), 1000);
+                    const int ko = 2 * (g & 7) + s;
+                    // block (ko, a): [ko][a] (parity 0) or [a][ko] (parity 1), 2 KiB each; of every block this thread
+                    // copies the 16-byte units h and h + 64 (one pointer increment per two copies, no index arithmetic:
+                    // the first version of this loop cost the compute warps a tenth of their issue slots)
+                    const uint8_t *src = cta_scratch + (size_t)(par ? ko : 16 * ko) * kBlk + h * 16;
+                    const size_t astride = par ? 16 * kBlk : kBlk;
+                    const uint32_t dst = sm + kOffRow + s * kRowBytes + h * 16;
+#pragma unroll
+                    for (int a = 0; a < 16; a++) {
+#if RPF_SOLO_HINTS
+                        cp_async16_hint(dst + a * kBlk, src, pol_rows);
+                        cp_async16_hint(dst + a * kBlk + 1024, src + 1024, pol_rows);
+#else
+                        cp_async16(dst + a * kBlk, src);
+                        cp_async16(dst + a * kBlk + 1024, src + 1024);
+#endif
+                        src += astride;
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sm + 8 * bar_rowfull(s)) : "memory");
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
         if (tid == kThreads) {
 #if RPF_SOLO_HINTS
             const uint64_t pol_raw = l2_policy_evict_first();
@@ -246,7 +296,7 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         }
         return;
     }
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");   // (240 - 168) x 256 = (168 - 24) x 128: exactly what the copy group gave back
 
     // ---- per-thread constants ----------------------------------------------------------------
     float2 tw1[15], tw2[15], twO[15];
@@ -275,13 +325,12 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
 #if RPF_SOLO_HINTS
     const uint64_t pol_keep = l2_policy_evict_last();
 #define RPF_SOLO_STG(p, v) stg_c32_hint((p), (v), pol_keep)
-#define RPF_SOLO_LDG(p) ldg_c32_hint((p), pol_keep)
 #else
 #define RPF_SOLO_STG(p, v) stg_c32((p), (v))
-#define RPF_SOLO_LDG(p) ldg_c32((p))
 #endif
     uint8_t *sbase = reinterpret_cast<uint8_t *>(scratch + (size_t)blockIdx.x * kBig + tid);   // my column of every block
     const uint32_t raw_ld = sm + kOffRaw + 2 * tid;              // + slot * 16 KiB + half * 512 + n1 * 1024
+    const uint32_t row_ld = sm + kOffRow + tid * 8;              // + s * 32 KiB + a * 2048: x[256 a + t]
     const uint32_t s1_st = sm + kOffS1 + tid * 128 + ((tid & 7) << 4);
     const uint32_t s1_ld = sm + kOffS1 + hi * 128 + ((((lo >> 1) ^ (hi & 7)) << 4) | ((lo & 1) << 3));   // + n2 * 2048
     const uint32_t s2_st = sm + kOffS2 + hi * 128 + lo * 8;                                              // + k2 * 2048
@@ -358,42 +407,39 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
             v[n1] = unpack_biased(raw[n1]);
             if (WINDOW) v[n1] = __fadd2_rn(v[n1], make_float2(-kBias, -kBias));   // byte - 127.0f, exact
         }
-        if (WINDOW) {
-            c32 y[16];
-            dft16_first_windowed(v, win);
-            dft16_second_a(v, y);
-            dft16_second_b(v, y);
-            fetch();
-            load_window((a + 1) & 15);                                           // for the next outer stage
-        } else {
-            radix(v, fetch);
-            v[0] = __fadd2_rn(v[0], make_float2(-16.0f * kBias, -16.0f * kBias));   // the bias survives in ko = 0 only (exact)
-        }
+        c32 y[16];
+        if (WINDOW) dft16_first_windowed(v, win); else dft16_first(v);
+        // blocks [ko][a] (parity 0) or [a][ko] (parity 1)
+        uint8_t *p = sbase + (par == 0 ? a * kBlk : a * (16 * kBlk));
+        // the 16 stores leave in four groups, each behind the radix-4 that produces its outputs ko = q + 4 k1: sixteen
+        // back to back fill the LSU queue, and whatever next overwrites one of their registers waits for it to drain
+        auto emit = [&](auto qc) {
+            constexpr int q = decltype(qc)::value;
 #pragma unroll
-        for (int k = 1; k < 16; k++) v[k] = cmul(v[k], twO[k - 1]);
-        if (par == 0) {                                          // blocks [ko][a]
-            uint8_t *p = sbase + a * kBlk;
-#pragma unroll
-            for (int ko = 0; ko < 16; ko++) RPF_SOLO_STG(p + ko * (16 * kBlk), v[ko]);
-        } else {                                                 // blocks [a][ko]
-            uint8_t *p = sbase + a * (16 * kBlk);
-#pragma unroll
-            for (int ko = 0; ko < 16; ko++) RPF_SOLO_STG(p + ko * kBlk, v[ko]);
-        }
-#pragma unroll
-        for (int k = 1; k < 16; k++) twO[k - 1] = cmul(twO[k - 1], w256_re(k), w256_im(k));
+            for (int k1 = 0; k1 < 4; k1++) {
+                const int ko = q + 4 * k1;
+                c32 o = y[ko];
+                if (!WINDOW && ko == 0) o = __fadd2_rn(o, make_float2(-16.0f * kBias, -16.0f * kBias));   // the bias survives in ko = 0 only (exact)
+                if (ko != 0) o = cmul(o, twO[ko - 1]);
+                if (par == 0) RPF_SOLO_STG(p + ko * (16 * kBlk), o); else RPF_SOLO_STG(p + ko * kBlk, o);
+                if (ko != 0) twO[ko - 1] = cmul(twO[ko - 1], w256_re(ko), w256_im(ko));
+            }
+        };
+        radix4_tw<0>(v[0], v[1], v[2], v[3], y[0], y[4], y[8], y[12]);
+        emit(std::integral_constant<int, 0>());
+        radix4_tw<1>(v[4], v[5], v[6], v[7], y[1], y[5], y[9], y[13]);
+        emit(std::integral_constant<int, 1>());
+        fetch();
+        if (WINDOW) load_window((a + 1) & 15);                                   // for the next outer stage
+        radix4_tw<2>(v[8], v[9], v[10], v[11], y[2], y[6], y[10], y[14]);
+        emit(std::integral_constant<int, 2>());
+        radix4_tw<3>(v[12], v[13], v[14], v[15], y[3], y[7], y[11], y[15]);
+        emit(std::integral_constant<int, 3>());
     };
-    // my 16 inputs x[256 a + t] of the inner transform ko (spectrum stored with parity `par`) -> registers
-    auto load_row = [&](c32 (&v)[16], int ko, int par) {
-        if (par == 0) {
-            const uint8_t *p = sbase + ko * (16 * kBlk);
-#pragma unroll
-            for (int a = 0; a < 16; a++) v[a] = RPF_SOLO_LDG(p + a * kBlk);
-        } else {
-            const uint8_t *p = sbase + ko * kBlk;
-#pragma unroll
-            for (int a = 0; a < 16; a++) v[a] = RPF_SOLO_LDG(p + a * (16 * kBlk));
-        }
+    // my 16 inputs x[256 a + t] of stream s of iteration g, staged by the helper warps -> registers
+    auto load_row = [&](c32 (&v)[16], int s, int g) {
+        mbar_wait(sm + 8 * bar_rowfull(s), (uint32_t)(g & 1));
+        lds64x16<2048>(row_ld + s * kStreamS, v);
     };
 
     // ---- prologue: the whole outer pass of my first spectrum; rows 0 and 1 on their way ------------------------
@@ -406,8 +452,8 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         warp_arrive(sm + 8 * bar_empty(pp & (kRawStg - 1)));
         if (pp < 7) fetch_raw(pp + 1, 0);
     }
+    warp_arrive(sm + 8 * kBarWritten);
     load_row(vA, 0, 0);
-    load_row(vB, 1, 0);
 
     const uint32_t rd = sm + 8 * bar_rd(0, 1);           // bar_rd(s, e) = rd + 8 (2 s + e - 1)
     int since_flush = 0;
@@ -417,11 +463,11 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         const int par = (j >> 3) & 1;
         if (i == 0) { reload_twO(); load_window(0); }     // the outer stages of this spectrum's successor start at a = 0
 
-        // ---- (A,1) --------------------------------------------------------------------------------
-        radix(vA, []() {});
+        // ---- (A,1) | row B ------------------------------------------------------------------------
+        radix(vA, [&]() { warp_arrive(sm + 8 * bar_rowfree(0)); load_row(vB, 1, j); });     // (row A has been consumed)
         post1(vA, 0);
         // ---- (B,1) | S1[A] ------------------------------------------------------------------------
-        radix(vB, [&]() { mbar_wait(rd, ph); lds64x16<2048>(s1_ld, vA); });
+        radix(vB, [&]() { warp_arrive(sm + 8 * bar_rowfree(1)); mbar_wait(rd, ph); lds64x16<2048>(s1_ld, vA); });
         post1(vB, 1);
         // ---- (A,2) | S1[B] ------------------------------------------------------------------------
         radix(vA, [&]() { mbar_wait(rd + 16, ph); lds64x16<2048>(s1_ld + kStreamS, vB); });
@@ -433,8 +479,7 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         outer(vB, 2 * i, par ^ 1, [&]() { fetch_raw(8 + j, 1); });
         outer(vB, 2 * i + 1, par ^ 1, [&]() {});
         warp_arrive(sm + 8 * bar_empty(j & (kRawStg - 1)));
-        // the rows of the next iteration: ko = 2i + 2, 2i + 3 of this spectrum, or 0, 1 of the next one
-        const int kon = (2 * i + 2) & 15, parn = par ^ (i == 7 ? 1 : 0);
+        if (i == 7) warp_arrive(sm + 8 * kBarWritten);    // the outer pass of the next spectrum is complete
         // ---- (A,3) | S2[B] ------------------------------------------------------------------------
         tmem_st_wait();                                   // (the stores of the previous iteration: long done)
         tmem_ld16(tm_acc + (2 * i) * 16, acc);
@@ -442,14 +487,12 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         tmem_ld_wait();
         power(vA);
         tmem_st16(tm_acc + (2 * i) * 16, acc);
-        load_row(vA, kon, parn);                          // lands under (B,3)
-        // ---- (B,3) ----------------------------------------------------------------------------------
+        // ---- (B,3) | row A of the next iteration -------------------------------------------------------
         tmem_ld16(tm_acc + (2 * i + 1) * 16, acc);
-        radix(vB, []() {});
+        radix(vB, [&]() { load_row(vA, 0, j + 1); });
         tmem_ld_wait();
         power(vB);
         tmem_st16(tm_acc + (2 * i + 1) * 16, acc);
-        load_row(vB, kon + 1, parn);                      // lands under (A,1) of the next iteration
 
         if (i == 7 && ++since_flush == kFlushSpectra) { tmem_st_wait(); flush(); since_flush = 0; }
     }
@@ -462,23 +505,39 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
 
 }  // namespace
 
+// RPF_SOLO_PERSIST = 1: while a context of this kind exists on the device, the L2 set-aside for persisting (evict_last)
+// lines is raised to what the device allows (79 MiB on the B200; the scratch is 74 MB), so that the raw stream and the
+// float64 rows cannot displace the scratch: DRAM writes 2.1 GB -> 0.17 GB per 2.1 GB of input.  The previous limit is
+// restored by rpf_solo65536_release().
 #ifndef RPF_SOLO_PERSIST
-#define RPF_SOLO_PERSIST 0
+#define RPF_SOLO_PERSIST 1
 #endif
-cudaError_t rpf_solo65536_configure()
+cudaError_t rpf_solo65536_configure(size_t *saved_limit)
 {
+    *saved_limit = (size_t)-1;
 #if RPF_SOLO_PERSIST
-    {   // L2 set-aside for persisting (evict_last) lines: as much as the device allows
+    {
         int dev = 0, maxp = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        if (maxp > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp);
-        fprintf(stderr, "solo65536: persisting L2 set-aside %d MiB\n", maxp >> 20);
+        size_t cur = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && maxp > 0 &&
+            cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess && cur < (size_t)maxp &&
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp) == cudaSuccess)
+            *saved_limit = cur;
+        cudaGetLastError();                        // best effort: without the set-aside the hints alone still work
     }
 #endif
     cudaError_t e = cudaFuncSetAttribute(solo65536_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(solo65536_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+}
+
+void rpf_solo65536_release(size_t saved_limit)
+{
+    if (saved_limit != (size_t)-1) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, saved_limit);
+        cudaGetLastError();
+    }
 }
 
 size_t rpf_solo65536_scratch_bytes(int grid) { return (size_t)grid * kBig * sizeof(float2); }
