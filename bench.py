@@ -319,6 +319,8 @@ def bench_config_device(pkg, torch, dev, local, name, n_bins, nspec, window, see
     pwr_dev = torch.zeros(n_bins, dtype=torch.float64, device=dev)
     ctx = pkg.Context(n_bins, window=window, device=local)
     ctx.set_stream(cur.cuda_stream)
+    if isinstance(kernel, dict):
+        kernel = kernel[ctx.plan_name]
     for _ in range(2):
         ctx.reset(nspec); ctx.push_device(stream_dev.data_ptr(), nbytes); ctx.finish_device(pwr_dev.data_ptr())
     torch.cuda.synchronize()
@@ -611,7 +613,8 @@ def main():
             configs.append(bench_config_device(pkg, torch, dev, local, "config3", N_BINS, 10000000, hann, 0x5EED + 3, 3,
                                                peak, "pipe4096_kernel<window>"))
             configs.append(bench_config_device(pkg, torch, dev, local, "config4", 65536, 100000, None, 0x5EED + 4, 3,
-                                               peak, "fourstep_outer_tma_kernel<16> + pipe4096_kernel<c32>"))
+                                               peak, {"solo65536": "solo65536_kernel (one launch, one CTA per spectrum)",
+                                                      "fourstep": "fourstep_outer_tma_kernel<16> + pipe4096_kernel<c32>"}))
         else:
             # config 5 as written: 8e7 spectra over 8 GPUs = 1e7 per GPU, one allreduce at the end
             n5 = 10000000

@@ -13,6 +13,7 @@ RPF_FLAG_PIPELINE = 8
 RPF_FLAG_CLUSTER65536 = 16
 RPF_FLAG_BATCHED4096 = 32
 RPF_FLAG_SOLO65536 = 64
+RPF_FLAG_FOURSTEP = 128
 RPF_MAX_DEVICES = 16
 
 EXPORTED_SYMBOLS = [

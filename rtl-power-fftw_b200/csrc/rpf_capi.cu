@@ -92,6 +92,7 @@ struct rpf_dev {
     int grid = 0, nrows = 0;
     int cluster_grid = 0;             // N = 65536: CTAs of the resident 16-CTA clusters (0: two-kernel four-step path)
     int solo_grid = 0;                // N = 65536: CTAs of the one-CTA-per-spectrum kernel (0: not selected)
+    int64_t solo_min = 0;             // ... which takes the launches of at least this many spectra
     float2 *d_solo = nullptr;         // ... and their private scratch, 512 KiB each
     size_t solo_saved_l2 = (size_t)-1;   // the device's persisting-L2 limit before this context raised it
     int rows_dirty = 0;               // private accumulator rows written since the last reset
@@ -240,8 +241,9 @@ int rows_touched(const rpf_ctx *c, const rpf_dev &d, int64_t nspec)
             if (c->use_pipen || c->use_batched) blocks = (blocks + 1) / 2;   // pairs of group iterations / ring slots
             break;
         case PLAN_FOURSTEP:
-            if (d.solo_grid) return (int)(nspec < d.solo_grid ? nspec : d.solo_grid) * 16;   // 16 rows per CTA that ran
-            return d.nrows;
+            if (d.solo_grid && nspec >= d.solo_min)
+                return (int)(nspec < d.solo_grid ? nspec : d.solo_grid) * 16;                // 16 rows per CTA that ran
+            return d.grid;
         case PLAN_BLUESTEIN: return d.nrows;
         default: blocks = nspec;
     }
@@ -280,7 +282,7 @@ int launch_spectra(rpf_ctx *c, rpf_dev &d, const uint8_t *src, int64_t nspec)
             CU(c, rpf_launch_bluestein(B, src + (size_t)done * c->spectrum_bytes, b, &n));
             d.launches += n;
         }
-    } else if (d.solo_grid) {
+    } else if (d.solo_grid && nspec >= d.solo_min) {
         RpfLaunch Ls = L;
         Ls.grid = d.solo_grid;
         CU(c, rpf_launch_solo65536(Ls, d.d_twiddle_big, d.d_solo));
@@ -403,16 +405,20 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
                 if (ncl * 16 > d.grid) ncl = d.grid / 16;          // (rows are sized by d.grid)
                 d.cluster_grid = ncl * 16;
             }
-            // RPF_FLAG_SOLO65536 (65536 bins, no window): one launch, one CTA per spectrum (solo65536.cu)
-            if (c->M == 16 && (cfg->flags & RPF_FLAG_SOLO65536)) {
+            // 65536 bins: one launch, one CTA per spectrum (solo65536.cu): 379 against 299 Gsamples/s for the two-kernel
+            // path on long launches.  A launch costs every CTA the time of a whole spectrum (~30 us) however few spectra
+            // there are, so short ones (the reference's 1,638,400-byte reads hold 12.5 spectra) stay on the two-kernel
+            // path; both add into the same private rows (row index mod 16 = outer bin on either path).
+            const uint32_t forced = cfg->flags & (RPF_FLAG_SOLO65536 | RPF_FLAG_FOURSTEP | RPF_FLAG_CLUSTER65536 | RPF_FLAG_LOCKSTEP);
+            if (c->M == 16 && (forced ? (forced & RPF_FLAG_SOLO65536) != 0 : cfg->scratch_mib == 0)) {
                 CU(c, rpf_solo65536_configure(&d.solo_saved_l2));
                 d.solo_grid = sms;
-                // rpf_config.scratch_mib bounds the scratch (512 KiB per CTA) and with it the CTA count (tuning runs)
-                if (cfg->scratch_mib > 0 && cfg->scratch_mib * 2 < d.solo_grid) d.solo_grid = cfg->scratch_mib * 2;
+                d.solo_min = (cfg->flags & RPF_FLAG_SOLO65536) ? 1 : 96;
+                // with the flag, rpf_config.scratch_mib bounds the scratch (512 KiB per CTA) and so the CTA count (tuning runs)
+                if (forced && cfg->scratch_mib > 0 && cfg->scratch_mib * 2 < d.solo_grid) d.solo_grid = cfg->scratch_mib * 2;
                 CU(c, cudaMalloc(&d.d_solo, rpf_solo65536_scratch_bytes(d.solo_grid)));
                 CU(c, cudaMemset(d.d_solo, 0, rpf_solo65536_scratch_bytes(d.solo_grid)));
                 d.cluster_grid = 0;
-                d.grid = d.solo_grid * 16;                          // private rows: 16 per CTA
             }
             break;
         }
@@ -433,6 +439,7 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
         CU(c, cudaMemcpy(d.d_window, cfg->window, sizeof(float) * N, cudaMemcpyHostToDevice));
     }
     d.nrows = d.grid * c->groups;
+    if (d.solo_grid * 16 > d.nrows) d.nrows = d.solo_grid * 16;       // 16 private rows per CTA of the solo kernel
     CU(c, cudaMalloc(&d.d_rows, sizeof(double) * (size_t)d.nrows * c->rowlen));
     CU(c, cudaMalloc(&d.d_pwr, sizeof(double) * N));
     CU(c, cudaMalloc(&d.d_tmp, sizeof(double) * 2 * N));

@@ -514,7 +514,7 @@ def test_cluster65536_matches_two_kernel_path_and_oracle(R):
     N = 65536
     s = stream(2 * N * R, seed=R * 13 + 5, mode=1)
     pc, done = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_CLUSTER65536)
-    pt, done_t = run_gpu(N, R, [s])
+    pt, done_t = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_FOURSTEP)
     assert done == done_t == R
     assert relmax(pc, pt) < 2e-6 and perbin(pc, pt) < 2e-5
     if R <= 9:
@@ -537,7 +537,7 @@ def test_solo65536_matches_two_kernel_path_and_oracle(R):
     with Context(N, flags=pkg.capi.RPF_FLAG_SOLO65536) as c:
         assert c.plan_name == "solo65536"
     ps, done = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_SOLO65536)
-    pt, done_t = run_gpu(N, R, [s])
+    pt, done_t = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_FOURSTEP)
     assert done == done_t == R
     # (per bin: with a handful of spectra some bins are orders of magnitude below the mean)
     assert relmax(ps, pt) < 2e-6 and perbin(ps, pt) < (2e-5 if R >= 9 else 1e-3)
@@ -556,7 +556,7 @@ def test_solo65536_window(R):
     w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32)
     s = stream(2 * N * R, seed=R + 71, mode=1)
     ps, done = run_gpu(N, R, [s], window=w, flags=pkg.capi.RPF_FLAG_SOLO65536)
-    pt, done_t = run_gpu(N, R, [s], window=w)
+    pt, done_t = run_gpu(N, R, [s], window=w, flags=pkg.capi.RPF_FLAG_FOURSTEP)
     assert done == done_t == R
     # (per bin: with a handful of spectra some bins are orders of magnitude below the mean)
     assert relmax(ps, pt) < 2e-6 and perbin(ps, pt) < (2e-5 if R >= 9 else 1e-3)
@@ -594,9 +594,36 @@ def test_solo65536_kats_pushes_and_reuse():
         assert done == R
         c.reset(R); c.push(s); p2, done = c.finish()
         assert done == R
-    pt, _ = run_gpu(N, R, [s])
+    pt, _ = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_FOURSTEP)
     assert relmax(p1, pt) < 2e-6 and perbin(p1, pt) < 2e-5
     assert relmax(p1, p2) < 1e-6
+
+
+def test_65536_default_mixes_both_paths():
+    """Without a flag a 65536-bin context sends launches of at least 96 spectra to the one-CTA-per-spectrum kernel and
+    shorter ones (the reference's 1,638,400-byte reads hold 12.5 spectra) to the two-kernel path; both add into the same
+    private rows.  One integration fed by pushes of both kinds must equal either path alone and the oracle on a prefix."""
+    N, R = 65536, 12 + 300 + 7 + 150
+    s = stream(2 * N * R, seed=4242, mode=1)
+    cuts = [0, 2 * N * 12, 2 * N * 312 + 1000, 2 * N * 319 + 1000, s.size]
+    with Context(N) as c:
+        assert c.plan_name == "solo65536"
+        c.reset(R)
+        l0 = c.kernel_launches
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            c.push(s[a:b])
+        launches = c.kernel_launches - l0
+        pm, done = c.finish()
+        assert done == R and launches == 2 + 1 + 2 + 1          # two-kernel, solo, two-kernel, solo
+        c.reset(8)
+        c.push(s[:2 * N * 8])
+        p8, _ = c.finish()
+    ps, _ = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_SOLO65536)
+    pt, _ = run_gpu(N, R, [s], flags=pkg.capi.RPF_FLAG_FOURSTEP)
+    assert relmax(pm, ps) < 2e-6 and perbin(pm, ps) < 2e-5
+    assert relmax(pm, pt) < 2e-6 and perbin(pm, pt) < 2e-5
+    po, _ = ol.oracle_run_stream(N, 8, s[:2 * N * 8], buf_length=2 * N * 8)
+    assert relmax(p8, po) < TOL
 
 
 @pytest.mark.parametrize("N,R", [(8192, 37), (16384, 300), (32768, 5), (65536, 1), (65536, 19), (65536, 700)])
@@ -607,8 +634,9 @@ def test_tma_outer_pass_is_bit_identical_to_the_plain_one(N, R, windowed):
     outer radix, with a window, for counts that leave column ranges without work or cross a scratch batch."""
     w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32) if windowed else None
     s = stream(2 * N * R, seed=N + R, mode=1)
-    pn, done = run_gpu(N, R, [s], window=w)
-    po, done_o = run_gpu(N, R, [s], window=w, flags=pkg.capi.RPF_FLAG_LOCKSTEP)
+    F = pkg.capi.RPF_FLAG_FOURSTEP                    # (65536 bins: keep both runs on the two-kernel path)
+    pn, done = run_gpu(N, R, [s], window=w, flags=F)
+    po, done_o = run_gpu(N, R, [s], window=w, flags=F | pkg.capi.RPF_FLAG_LOCKSTEP)
     assert done == done_o == R
     assert np.array_equal(pn, po)
     if R <= 5:
