@@ -145,6 +145,7 @@ struct rpf_ctx {
     std::vector<Pending> pending;     // host->device copies of the last push that were not waited for yet
 
     int64_t repeats = INT64_MAX, repeats_done = 0;
+    bool early_reduced = false;       // the push that completed the integration has already enqueued the reduction into h_pwr
     char err[256] = "";
 };
 
@@ -669,6 +670,7 @@ int rpf_reset(rpf_ctx *c, int64_t repeats)
     c->repeats = repeats;
     c->repeats_done = 0;
     c->carry_bytes = 0;
+    c->early_reduced = false;
     return RPF_OK;
 }
 
@@ -706,6 +708,7 @@ int rpf_push(rpf_ctx *c, const uint8_t *bytes, size_t len)
     if (parts > nd) parts = nd;
     if ((int64_t)parts > nspec) parts = (int)nspec;
     size_t consumed = 0;                                         // bytes of (carry + new) dealt so far
+    cudaEvent_t in_place_read = nullptr;                         // set when a kernel reads the caller's buffer itself
     for (int p = 0; p < parts; p++) {
         const int64_t s0 = nspec * p / parts, s1 = nspec * (p + 1) / parts;
         const size_t part_bytes = (size_t)(s1 - s0) * sb;
@@ -725,6 +728,27 @@ int rpf_push(rpf_ctx *c, const uint8_t *bytes, size_t len)
             // (the kernels read the pinned bounce buffer in place -- TMA over PCIe -- so there is no separate copy
             // operation either: for ~100 KB the launch gaps of a memcpy cost more than the transfer)
             CU(c, cudaEventSynchronize(d.ev_consumed[s]));       // bounce slot free (3 pushes ago)
+            // A short push that COMPLETES the integration out of a page-locked buffer (the reference-shaped Datastore
+            // page-locks its Buffers; config 1 is one such read) skips even the bounce copy: the kernel reads the
+            // caller's buffer in place and the call returns when it has -- the caller would wait for this kernel in
+            // rpf_finish anyway, and ~10 us of host memcpy leave the critical path.  Other short pushes keep the
+            // bounce copy, which lets the caller go on while the GPU works.
+            bool in_place = false;
+            if (from_carry == 0 && parts == 1 && c->repeats_done + nspec >= c->repeats && (((uintptr_t)src) & 15) == 0) {
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, src) == cudaSuccess)
+                    in_place = at.type == cudaMemoryTypeHost && at.devicePointer == (const void *)src;
+                else
+                    cudaGetLastError();
+            }
+            if (in_place) {
+                r = launch_spectra(c, d, src, s1 - s0);
+                if (r) return r;
+                CU(c, cudaEventRecord(d.ev_consumed[s], d.stream));
+                in_place_read = d.ev_consumed[s];                // waited for below: `bytes` is free on return
+                consumed += part_bytes;
+                continue;
+            }
             if (from_carry) memcpy(d.h_bounce[s], c->h_carry[cs], from_carry);
             memcpy(d.h_bounce[s] + from_carry, src, from_new);
             r = launch_spectra(c, d, d.h_bounce[s], s1 - s0);
@@ -755,6 +779,16 @@ int rpf_push(rpf_ctx *c, const uint8_t *bytes, size_t len)
         c->carry_bytes = tail;
     }
     c->cslot = cn;
+    // The push that completes the integration (src/datastore.cxx:67: the worker stops here) enqueues the reduction
+    // of the private rows right behind its kernels instead of leaving it to rpf_finish: one launch latency less
+    // between the last FFT kernel and the result (config 1: a single read per integration).
+    if (c->repeats_done >= c->repeats && c->devs.size() == 1 && c->comm_nranks == 1 && !c->early_reduced) {
+        CU(c, cudaSetDevice(c->devs[0].device));
+        r = reduce_device(c, c->devs[0], c->h_pwr);
+        if (r) return r;
+        c->early_reduced = true;
+    }
+    if (in_place_read) CU(c, cudaEventSynchronize(in_place_read));
     if (!c->pipelined) return drain_pending(c);                  // caller may now reuse `bytes`
     return RPF_OK;                                               // pipelined: `bytes` is free after the NEXT call
 }
@@ -873,8 +907,10 @@ int rpf_finish(rpf_ctx *c, double *pwr_out, int64_t *repeats_done)
     if (direct) {
         // one GPU: the reduction writes pwr[] straight into device-visible pinned host memory (no D2H operation)
         CU(c, cudaSetDevice(d0.device));
-        r = reduce_device(c, d0, c->h_pwr);
-        if (r) return r;
+        if (!c->early_reduced) {                                 // (else: enqueued by the push that completed the integration)
+            r = reduce_device(c, d0, c->h_pwr);
+            if (r) return r;
+        }
     } else if (pwr_out) {
         r = reduce_all(c, nullptr);
         if (r) return r;

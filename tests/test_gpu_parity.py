@@ -177,6 +177,34 @@ def test_config1_reference_shape():
     assert np.array_equal(pg, pg2)                   # bytes past 2*N*repeats have no effect
 
 
+@pytest.mark.parametrize("N,nbytes,R", [(512, 114688, 100), (4096, 16384 * 16, 30), (64, 4096, 32)])
+def test_short_push_from_page_locked_memory_is_read_in_place(N, nbytes, R):
+    """A short push that completes the integration out of page-locked memory (the reference-shaped Datastore page-locks
+    its Buffers; config 1 is one such read) is read by the kernel in place, without the bounce copy: same bits as the
+    same bytes pushed from pageable memory, the buffer may be overwritten as soon as rpf_push has returned, and a push
+    that does NOT complete the integration still takes the bounce copy (so the caller is not held up)."""
+    import ctypes as C
+    ptr = C.c_void_p()
+    assert pkg.lib().rpf_host_alloc(C.byref(ptr), nbytes) == 0
+    try:
+        pkg.lib().rpf_synth_fill_host(ptr, nbytes, 0, 0x5EED + 1, 1)
+        pinned = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(nbytes,))
+        pageable = pinned.copy()
+        with Context(N) as c:
+            c.reset(R); c.push(pageable); p0, d0 = c.finish()
+            c.reset(R); c.push_ptr(ptr.value, nbytes); pinned[:] = 0; p1, d1 = c.finish()     # overwritten right after the push
+            pinned[:] = pageable
+            half = (R // 2) * 2 * N
+            c.reset(R); c.push_ptr(ptr.value, half); c.push_ptr(ptr.value + half, nbytes - half); p2, d2 = c.finish()
+        assert d0 == d1 == d2 == R
+        assert np.array_equal(p0, p1)
+        assert relmax(p0, p2) < 1e-6                  # (two launches: the float32 first-level sums are grouped differently)
+        po, _ = ol.oracle_run_stream(N, R, pageable, buf_length=nbytes)
+        assert perbin(p0, po) < TOL
+    finally:
+        pkg.lib().rpf_host_free(ptr)
+
+
 @pytest.mark.parametrize("N,R", [(4096, 1), (4096, 2), (4096, 3), (4096, 295), (4096, 297), (4096, 593), (8192, 1),
                                  (8192, 149), (65536, 1), (65536, 9), (65536, 10), (65536, 19)])
 def test_tail_shapes_of_the_pipelined_kernel(N, R):
@@ -614,7 +642,7 @@ def test_65536_default_mixes_both_paths():
             c.push(s[a:b])
         launches = c.kernel_launches - l0
         pm, done = c.finish()
-        assert done == R and launches == 2 + 1 + 2 + 1          # two-kernel, solo, two-kernel, solo
+        assert done == R and launches == 2 + 1 + 2 + 1 + 1      # two-kernel, solo, two-kernel, solo; + the reduction, enqueued by the push that completes the integration
         c.reset(8)
         c.push(s[:2 * N * 8])
         p8, _ = c.finish()
