@@ -243,7 +243,7 @@ int rows_touched(const rpf_ctx *c, const rpf_dev &d, int64_t nspec)
             break;
         case PLAN_FOURSTEP:
             if (d.solo_grid && nspec >= d.solo_min)
-                return (int)(nspec < d.solo_grid ? nspec : d.solo_grid) * 16;                // 16 rows per CTA that ran
+                return (int)(nspec < d.solo_grid ? nspec : d.solo_grid) * c->M;              // M rows per CTA that ran
             return d.grid;
         case PLAN_BLUESTEIN: return d.nrows;
         default: blocks = nspec;
@@ -285,7 +285,7 @@ int launch_spectra(rpf_ctx *c, rpf_dev &d, const uint8_t *src, int64_t nspec)
         }
     } else if (d.solo_grid && nspec >= d.solo_min) {
         RpfLaunch Ls = L;
-        Ls.grid = d.solo_grid;
+        Ls.grid = d.solo_grid; Ls.M = c->M;
         CU(c, rpf_launch_solo65536(Ls, d.d_twiddle_big, d.d_solo));
         d.launches++;
     } else if (d.cluster_grid) {
@@ -411,14 +411,14 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
             // there are, so short ones (the reference's 1,638,400-byte reads hold 12.5 spectra) stay on the two-kernel
             // path; both add into the same private rows (row index mod 16 = outer bin on either path).
             const uint32_t forced = cfg->flags & (RPF_FLAG_SOLO65536 | RPF_FLAG_FOURSTEP | RPF_FLAG_CLUSTER65536 | RPF_FLAG_LOCKSTEP);
-            if (c->M == 16 && (forced ? (forced & RPF_FLAG_SOLO65536) != 0 : cfg->scratch_mib == 0)) {
+            if (forced ? (forced & RPF_FLAG_SOLO65536) != 0 : cfg->scratch_mib == 0) {
                 CU(c, rpf_solo65536_configure(&d.solo_saved_l2));
                 d.solo_grid = sms;
                 d.solo_min = (cfg->flags & RPF_FLAG_SOLO65536) ? 1 : 96;
-                // with the flag, rpf_config.scratch_mib bounds the scratch (512 KiB per CTA) and so the CTA count (tuning runs)
-                if (forced && cfg->scratch_mib > 0 && cfg->scratch_mib * 2 < d.solo_grid) d.solo_grid = cfg->scratch_mib * 2;
-                CU(c, cudaMalloc(&d.d_solo, rpf_solo65536_scratch_bytes(d.solo_grid)));
-                CU(c, cudaMemset(d.d_solo, 0, rpf_solo65536_scratch_bytes(d.solo_grid)));
+                // with the flag, rpf_config.scratch_mib bounds the scratch (32 M KiB per CTA) and so the CTA count (tuning runs)
+                if (forced && cfg->scratch_mib > 0 && cfg->scratch_mib * (32 / c->M) < d.solo_grid) d.solo_grid = cfg->scratch_mib * (32 / c->M);
+                CU(c, cudaMalloc(&d.d_solo, rpf_solo65536_scratch_bytes(c->M, d.solo_grid)));
+                CU(c, cudaMemset(d.d_solo, 0, rpf_solo65536_scratch_bytes(c->M, d.solo_grid)));
                 d.cluster_grid = 0;
             }
             break;
@@ -440,7 +440,7 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
         CU(c, cudaMemcpy(d.d_window, cfg->window, sizeof(float) * N, cudaMemcpyHostToDevice));
     }
     d.nrows = d.grid * c->groups;
-    if (d.solo_grid * 16 > d.nrows) d.nrows = d.solo_grid * 16;       // 16 private rows per CTA of the solo kernel
+    if (d.solo_grid * c->M > d.nrows) d.nrows = d.solo_grid * c->M;   // M private rows per CTA of the solo kernel
     CU(c, cudaMalloc(&d.d_rows, sizeof(double) * (size_t)d.nrows * c->rowlen));
     CU(c, cudaMalloc(&d.d_pwr, sizeof(double) * N));
     CU(c, cudaMalloc(&d.d_tmp, sizeof(double) * 2 * N));
@@ -941,7 +941,7 @@ const char *rpf_plan_name(const rpf_ctx *c)
     if (c->plan == PLAN_BLUESTEIN) return c->blueM == c->N ? "gfft" : "bluestein";
     if (c->plan == PLAN_FUSED3) return c->usepipe ? "pipe4096" : c->use_batched ? "pipe4096_batched" : c->use_pipen ? "pipen" : "fused3";
     if (c->plan == PLAN_FOURSTEP)
-        return !c->devs.empty() && c->devs[0].solo_grid ? "solo65536" : !c->devs.empty() && c->devs[0].cluster_grid ? "cluster65536" : c->old_outer ? "fourstep_plain_outer" : "fourstep";
+        return !c->devs.empty() && c->devs[0].solo_grid ? (c->M == 16 ? "solo65536" : "solo") : !c->devs.empty() && c->devs[0].cluster_grid ? "cluster65536" : c->old_outer ? "fourstep_plain_outer" : "fourstep";
     return c->plan == PLAN_SMALL ? "small" : "direct";
 }
 

@@ -43,12 +43,12 @@ cudaError_t rpf_launch_pipe4096_small(int N, const RpfLaunch &L);
 cudaError_t rpf_cluster65536_configure(int *max_clusters);
 cudaError_t rpf_launch_cluster65536(const RpfLaunch &L, const float2 *twiddle_big);
 
-// N = 65536 without a window in one launch, one CTA per spectrum: thread-private hand-off of the outer radix-16 through an
-// L2-resident scratch (rpf_solo65536_scratch_bytes(grid) bytes), accumulators in tensor memory.  L.grid = CTAs,
-// L.rows = 16 rows of 4096 doubles per CTA (row 16 c + ko).
+// N = M * 4096 (M = 2 ... 16) in one launch, one CTA per spectrum: thread-private hand-off of the outer radix-M through an
+// L2-resident scratch (rpf_solo65536_scratch_bytes(M, grid) bytes), accumulators in tensor memory.  L.M = M, L.grid = CTAs,
+// L.rows = M rows of 4096 doubles per CTA (row M c + ko).
 cudaError_t rpf_solo65536_configure(size_t *saved_persisting_l2_limit);   // raises the device's persisting-L2 set-aside
 void rpf_solo65536_release(size_t saved_persisting_l2_limit);              // ... and puts it back
-size_t rpf_solo65536_scratch_bytes(int grid);
+size_t rpf_solo65536_scratch_bytes(int M, int grid);
 cudaError_t rpf_launch_solo65536(const RpfLaunch &L, const float2 *twiddle_big, float2 *scratch);
 
 // N = 4096 with pass 1 on the tensor cores (tcgen05.mma, fp16 hi+lo DFT-16 matrix; raw bytes, no window): experiment

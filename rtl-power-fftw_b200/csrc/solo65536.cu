@@ -1,4 +1,7 @@
-// solo65536.cu -- N = 65536 in ONE launch, one CTA per spectrum, thread-private hand-off.
+// solo65536.cu -- N = M * 4096 (M = 2, 4, 8, 16: 8192 ... 65536 bins) in ONE launch, one CTA per spectrum, thread-private
+// hand-off.  Written for 65536 bins (M = 16), which the comments below describe; the outer radix
+// is a template parameter (M < 16: an outer stage is 16 / M radix-M butterflies over as many values of a, a spectrum has
+// M / 2 iterations, the scratch M x 16 blocks).
 //
 // n = 4096 n1 + m, k = ko + 16 k'.  The two-kernel four-step path writes the outer radix-16 to a complex64 scratch and
 // reads it back (2 + 8 + 8 B of DRAM traffic per sample); the cluster kernel scatters it through distributed shared
@@ -14,9 +17,10 @@
 //     cp.async (LDGSTS) into a 32 KiB row slot per stream, two to three stages before pass 1 needs the row (a first
 //     version loaded the rows with ld.global straight into the idle stream's registers: one stage of distance is less
 //     than the L2 latency under load, 10 % of all warp samples sat on the first use);
-//   * the scratch is reused IN PLACE: spectrum s lives as [ko][a] blocks of 2 KiB, spectrum s + 1 as [a][ko] -- outer
-//     stage a of the next spectrum overwrites exactly the row ko = a of the current one, which was consumed one
-//     iteration earlier (rows 2i, 2i+1 are read at the end of iteration i - 1, stages a = 2i, 2i+1 run in iteration i);
+//   * the scratch is reused IN PLACE: spectrum s lives as [ko][a] blocks of 2 KiB, spectrum s + 1 with the fields
+//     ko >> 1 and a >> (5 - log2 M) of the block index exchanged -- the outer stages of iteration i of the next spectrum
+//     (a >> (5 - log2 M) = i) overwrite exactly the rows ko = 2i, 2i + 1 of the current one, consumed an iteration
+//     earlier, in either layout;
 //   * a CTA that runs all 16 inner transforms needs 16 x 16 accumulators per thread: they live in TENSOR MEMORY used
 //     as a per-thread scratchpad (256 KiB = 256 floats per thread: tcgen05.ld.x16, 32 FFMA, tcgen05.st.x16 per inner
 //     transform), flushed to the CTA's float64 rows every 128 spectra like everywhere else;
@@ -40,8 +44,6 @@
 namespace {
 
 constexpr int kN = 4096;                      // inner transform
-constexpr int kM = 16;                        // outer radix
-constexpr int kBig = kN * kM;
 constexpr int kThreads = 256;                 // compute threads (8 warps)
 constexpr int kLaunchThreads = kThreads + 128;
 #ifndef RPF_SOLO_FLUSH
@@ -50,8 +52,30 @@ constexpr int kLaunchThreads = kThreads + 128;
 constexpr int kFlushSpectra = RPF_SOLO_FLUSH; // float32 partial sums over at most this many spectra
 constexpr int kRowBytes = kN * 8;             // one complex64 row of the inner transform
 constexpr int kBlk = 256 * 8;                 // scratch block: 256 threads x one complex64 = 2 KiB
-constexpr int kPairChunk = 1024;              // raw bytes per n1 and iteration: 2 outer stages x 256 columns x 2 B
-constexpr int kRawSlot = kM * kPairChunk;     // 16 KiB
+constexpr int kRawSlot = 16384;               // raw bytes per iteration: 2 outer stages x 16 values x 256 columns x 2 B
+// geometry for outer radix M
+template <int M>
+struct Geo {
+    static_assert(M == 2 || M == 4 || M == 8 || M == 16, "outer radix");
+    static constexpr int kBig = kN * M;           // bins
+    static constexpr int C = 16 / M;              // values of a (columns per thread) per outer stage
+    static constexpr int AL = 32 / M;             // values of a per iteration = 2^(5 - log2 M)
+    static constexpr int IPS = M / 2;             // iterations per spectrum (two inner transforms each)
+    static constexpr int kChunk = kRawSlot / M;   // raw bytes per n1 and iteration
+    // Block index of (ko, a) in the two layouts of the in-place scratch.  Layout 0 is [ko][a]; layout 1 exchanges the
+    // fields ko >> 1 and a / AL (what an iteration consumes <-> what its outer stages produce), so that the blocks the
+    // outer stages of iteration i write (a / AL = i, every ko) are the blocks of the rows ko = 2i, 2i + 1 in the other
+    // layout.  blk1 = g1(ko) + f1(a).  M = 16 (AL = 2) uses the plain transpose [a][ko], which has the same property.
+#ifndef RPF_SOLO_L1_TRANSPOSE16
+#define RPF_SOLO_L1_TRANSPOSE16 1
+#endif
+    static constexpr bool kT16 = RPF_SOLO_L1_TRANSPOSE16 && M == 16;
+    static __host__ __device__ constexpr int blk0(int ko, int a) { return ko * 16 + a; }
+    static __host__ __device__ constexpr int g1(int ko) { return kT16 ? ko : (ko & 1) * 16 + (ko >> 1) * AL; }
+    static __host__ __device__ constexpr int f1(int a) { return kT16 ? a * 16 : (a / AL) * 32 + (a % AL); }
+    static constexpr int kRun = kT16 ? 1 : AL;    // layout 1: a row is runs of kRun blocks ...
+    static constexpr int kRunStride1 = kT16 ? 16 : 32;   // ... this many blocks apart (layout 0: contiguous)
+};
 #ifndef RPF_SOLO_RAWSTG
 #define RPF_SOLO_RAWSTG 2
 #endif
@@ -76,22 +100,27 @@ constexpr int kTmemSlotOff = 8 * (kBarWritten + 5);   // uint32: TMEM base addre
 static_assert(kTmemSlotOff + 4 <= kHdr && (kRawStg & (kRawStg - 1)) == 0, "header");
 constexpr int kTmemCols = 512;
 
-// W_256^k, k = 0..15 (cos, -sin)
-__host__ __device__ constexpr float w256_re(int k)
+// W_256^j (cos, -sin) for the exponents the twiddle recurrence needs: the step from one outer stage to the next is
+// W_{M^2}^{ko} = W_256^{ko 256 / M^2}: j = ko (M = 16), 4 ko (8), 16 ko (4), 64 (2)
+__host__ __device__ constexpr float w256_re(int j)
 {
-    return k == 0 ? 1.0f : k == 1 ? 0.99969881869620425f : k == 2 ? 0.99879545620517241f : k == 3 ? 0.99729045667869021f
-         : k == 4 ? 0.99518472667219693f : k == 5 ? 0.99247953459870997f : k == 6 ? 0.98917650996478101f
-         : k == 7 ? 0.98527764238894122f : k == 8 ? 0.98078528040323043f : k == 9 ? 0.97570213003852857f
-         : k == 10 ? 0.97003125319454397f : k == 11 ? 0.96377606579543984f : k == 12 ? 0.95694033573220882f
-         : k == 13 ? 0.94952818059303667f : k == 14 ? 0.94154406518302081f : 0.93299279883473896f;
+    return j == 0 ? 1.0f : j == 1 ? 0.99969881869620425f : j == 2 ? 0.99879545620517241f : j == 3 ? 0.99729045667869021f
+         : j == 4 ? 0.99518472667219693f : j == 5 ? 0.99247953459870997f : j == 6 ? 0.98917650996478101f
+         : j == 7 ? 0.98527764238894122f : j == 8 ? 0.98078528040323043f : j == 9 ? 0.97570213003852857f
+         : j == 10 ? 0.97003125319454397f : j == 11 ? 0.96377606579543984f : j == 12 ? 0.95694033573220882f
+         : j == 13 ? 0.94952818059303667f : j == 14 ? 0.94154406518302081f : j == 15 ? 0.93299279883473896f
+         : j == 16 ? 0.92387953251128674f : j == 20 ? 0.88192126434835505f : j == 24 ? 0.83146961230254524f
+         : j == 28 ? 0.77301045336273699f : j == 32 ? 0.70710678118654757f : j == 48 ? 0.38268343236508984f : 0.0f;
 }
-__host__ __device__ constexpr float w256_im(int k)
+__host__ __device__ constexpr float w256_im(int j)
 {
-    return k == 0 ? 0.0f : k == 1 ? -0.024541228522912288f : k == 2 ? -0.049067674327418015f : k == 3 ? -0.073564563599667426f
-         : k == 4 ? -0.098017140329560604f : k == 5 ? -0.1224106751992162f : k == 6 ? -0.14673047445536175f
-         : k == 7 ? -0.17096188876030122f : k == 8 ? -0.19509032201612825f : k == 9 ? -0.2191012401568698f
-         : k == 10 ? -0.24298017990326387f : k == 11 ? -0.26671275747489837f : k == 12 ? -0.29028467725446233f
-         : k == 13 ? -0.31368174039889152f : k == 14 ? -0.33688985339222005f : -0.35989503653498811f;
+    return j == 0 ? 0.0f : j == 1 ? -0.024541228522912288f : j == 2 ? -0.049067674327418015f : j == 3 ? -0.073564563599667426f
+         : j == 4 ? -0.098017140329560604f : j == 5 ? -0.1224106751992162f : j == 6 ? -0.14673047445536175f
+         : j == 7 ? -0.17096188876030122f : j == 8 ? -0.19509032201612825f : j == 9 ? -0.2191012401568698f
+         : j == 10 ? -0.24298017990326387f : j == 11 ? -0.26671275747489837f : j == 12 ? -0.29028467725446233f
+         : j == 13 ? -0.31368174039889152f : j == 14 ? -0.33688985339222005f : j == 15 ? -0.35989503653498811f
+         : j == 16 ? -0.38268343236508978f : j == 20 ? -0.47139673682599764f : j == 24 ? -0.55557023301960218f
+         : j == 28 ? -0.63439328416364549f : j == 32 ? -0.70710678118654746f : j == 48 ? -0.92387953251128674f : -1.0f;
 }
 
 // RPF_SOLO_HINTS = 1: L2 eviction priorities -- the raw stream is read once (evict_first), the scratch is what should
@@ -101,11 +130,13 @@ __host__ __device__ constexpr float w256_im(int k)
 #define RPF_SOLO_HINTS 1
 #endif
 
-template <int STRIDE>
+// raw[c * M + n1] = the byte pair of column c, digit n1: columns 512 bytes apart, digits CHUNK bytes apart
+template <int M, int CHUNK>
 __device__ __forceinline__ void lds16x16(uint32_t base, uint32_t (&raw)[16])
 {
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(raw[n1]) : "r"(base + n1 * STRIDE));
+    for (int j = 0; j < 16; j++)
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(raw[j]) : "r"(base + (j / M) * 512 + (j % M) * CHUNK));
 }
 template <int STRIDE>
 __device__ __forceinline__ void lds64x16(uint32_t base, c32 (&v)[16])
@@ -188,9 +219,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16])
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// CTA c takes the spectra c, c + grid, ... of the launch.  scratch: 65536 complex64 per CTA; rows: 16 private rows of
-// 4096 doubles per CTA (row 16 c + ko = outer bin ko, natural order k'), summed by reduce_rows_fourstep().
-template <bool WINDOW>
+// CTA c takes the spectra c, c + grid, ... of the launch.  scratch: M * 4096 complex64 per CTA; rows: M private rows of
+// 4096 doubles per CTA (row M c + ko = outer bin ko, natural order k'), summed by reduce_rows_fourstep().
+template <bool WINDOW, int M>
 __global__ void __launch_bounds__(kLaunchThreads, 1)
 solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 *__restrict__ twiddle,
                  const float2 *__restrict__ twbig, const float *__restrict__ window, float2 *__restrict__ scratch,
@@ -200,12 +231,14 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
     const uint32_t sm = smem_u32(smem);
     const int tid = threadIdx.x;
     const int lo = tid & 15, hi = tid >> 4;       // pass 2: (k1 = lo, n3 = hi); pass 3: (k1 = lo, k2 = hi)
+    using G = Geo<M>;
+    constexpr int kBig = G::kBig, C = G::C, AL = G::AL, IPS = G::IPS, kChunk = G::kChunk;
 
     // ---- work range ------------------------------------------------------------------------
     const int mine = (int)((nspec - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x);   // >= 1: the host launches no idle CTA
     if (mine <= 0) return;
-    const int nit = 8 * mine;
-    const int npairs = 8 + nit;                   // raw pair slots consumed: 8 in the prologue, one per iteration
+    const int nit = IPS * mine;
+    const int npairs = IPS + nit;                 // raw pair slots consumed: IPS in the prologue, one per iteration
     auto spectrum_of = [&](int idx) { return (int64_t)blockIdx.x + (int64_t)gridDim.x * min(idx, mine - 1); };
 
     if (tid == 0) {
@@ -235,7 +268,7 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
     if (tid >= kThreads) {                             // the copy warp group
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (tid >= kThreads + 32 && tid < kThreads + 32 + kHelpers) {
-            // Row staging: generation g = the rows ko = 2i, 2i + 1 (i = g & 7) of my spectrum number g >> 3, wanted by
+            // Row staging: generation g = the rows ko = 2i, 2i + 1 (i = g % IPS) of my spectrum number g / IPS, wanted by
             // iteration g.  A row is fetched as soon as its slot has been read for generation g - 1 (a whole iteration
             // before it is needed); only the first two rows of a spectrum also have to wait for the last outer stages of
             // that spectrum (`written`, once per spectrum), which leaves them two to three stages.
@@ -245,28 +278,29 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
             const uint64_t pol_rows = l2_policy_evict_last();
 #endif
             for (int g = 0; g <= nit; g++) {       // (generation nit is never transformed: the loop stays branch-free)
-                const int par = (g >> 3) & 1;
+                const int gs = g / IPS, gi = g % IPS, par = gs & 1;
 #pragma unroll 1
                 for (int s = 0; s < 2; s++) {
                     if (g > 0) mbar_wait_parked(sm + 8 * bar_rowfree(s), (uint32_t)((g - 1) & 1), 1000);
-                    if (s == 0 && (g & 7) == 0) mbar_wait_parked(sm + 8 * kBarWritten, (uint32_t)((g >> 3) & 1), 1000);
-                    const int ko = 2 * (g & 7) + s;
-                    // block (ko, a): [ko][a] (parity 0) or [a][ko] (parity 1), 2 KiB each; of every block this thread
-                    // copies the 16-byte units h and h + 64 (one pointer increment per two copies, no index arithmetic:
-                    // the first version of this loop cost the compute warps a tenth of their issue slots)
-                    const uint8_t *src = cta_scratch + (size_t)(par ? ko : 16 * ko) * kBlk + h * 16;
-                    const size_t astride = par ? 16 * kBlk : kBlk;
+                    if (s == 0 && gi == 0) mbar_wait_parked(sm + 8 * kBarWritten, (uint32_t)(gs & 1), 1000);
+                    // blocks (ko = 2 gi + s, a), a = 0..15, 2 KiB each: 16 consecutive ones in layout 0, runs of kRun blocks
+                    // kRunStride1 apart in layout 1; of every block this thread copies the 16-byte units h and h + 64 (one
+                    // pointer increment per run, no index arithmetic: the first version of this loop cost the compute
+                    // warps a tenth of their issue slots)
+                    constexpr int RUN = G::kRun;
+                    const uint8_t *src = cta_scratch + (size_t)(par ? G::g1(2 * gi + s) : G::blk0(2 * gi + s, 0)) * kBlk + h * 16;
+                    const size_t run_stride = par ? G::kRunStride1 * kBlk : RUN * kBlk;
                     const uint32_t dst = sm + kOffRow + s * kRowBytes + h * 16;
 #pragma unroll
                     for (int a = 0; a < 16; a++) {
 #if RPF_SOLO_HINTS
-                        cp_async16_hint(dst + a * kBlk, src, pol_rows);
-                        cp_async16_hint(dst + a * kBlk + 1024, src + 1024, pol_rows);
+                        cp_async16_hint(dst + a * kBlk, src + (a % RUN) * kBlk, pol_rows);
+                        cp_async16_hint(dst + a * kBlk + 1024, src + (a % RUN) * kBlk + 1024, pol_rows);
 #else
-                        cp_async16(dst + a * kBlk, src);
-                        cp_async16(dst + a * kBlk + 1024, src + 1024);
+                        cp_async16(dst + a * kBlk, src + (a % RUN) * kBlk);
+                        cp_async16(dst + a * kBlk + 1024, src + (a % RUN) * kBlk + 1024);
 #endif
-                        src += astride;
+                        if (a % RUN == RUN - 1) src += run_stride;
                     }
                     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sm + 8 * bar_rowfull(s)) : "memory");
                 }
@@ -280,16 +314,16 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
             for (int p = 0; p < npairs; p++) {
                 const int slot = p & (kRawStg - 1);
                 if (p >= kRawStg) mbar_wait(sm + 8 * bar_empty(slot), (uint32_t)((p / kRawStg - 1) & 1));
-                // pair p: outer stages a = 2 (p & 7), 2 (p & 7) + 1 of my spectrum number p >> 3 (one past the end: re-read)
-                const uint8_t *src = bytes + (size_t)spectrum_of(p >> 3) * (2 * kBig) + (size_t)(p & 7) * kPairChunk;
+                // pair p: the two outer stages of iteration p % IPS of my spectrum number p / IPS (one past the end: re-read)
+                const uint8_t *src = bytes + (size_t)spectrum_of(p / IPS) * (2 * kBig) + (size_t)(p % IPS) * kChunk;
                 const uint32_t bar = sm + 8 * bar_full(slot), dst = sm + kOffRaw + slot * kRawSlot;
                 mbar_expect_tx(bar, kRawSlot);
 #pragma unroll
-                for (int n1 = 0; n1 < kM; n1++) {
+                for (int n1 = 0; n1 < M; n1++) {
 #if RPF_SOLO_HINTS
-                    tma_load_1d_hint(dst + n1 * kPairChunk, src + (size_t)n1 * 2 * kN, kPairChunk, bar, pol_raw);
+                    tma_load_1d_hint(dst + n1 * kChunk, src + (size_t)n1 * 2 * kN, kChunk, bar, pol_raw);
 #else
-                    tma_load_1d(dst + n1 * kPairChunk, src + (size_t)n1 * 2 * kN, kPairChunk, bar);
+                    tma_load_1d(dst + n1 * kChunk, src + (size_t)n1 * 2 * kN, kChunk, bar);
 #endif
                 }
             }
@@ -299,15 +333,16 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
     asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");   // (240 - 168) x 256 = (168 - 24) x 128: exactly what the copy group gave back
 
     // ---- per-thread constants ----------------------------------------------------------------
-    float2 tw1[15], tw2[15], twO[15];
+    float2 tw1[15], tw2[15], twO[16];                            // twO[c M + ko] (ko = 0 unused)
 #pragma unroll
     for (int k = 1; k < 16; k++) {
         tw1[k - 1] = twiddle[(tid * k) & (kN - 1)];             // W_4096^{t k1}
         tw2[k - 1] = twiddle[(hi * k * 16) & (kN - 1)];         // W_256^{n3 k2}
     }
-    auto reload_twO = [&]() {                                    // W_65536^{t ko}: column m = t (a = 0)
+    auto reload_twO = [&]() {                                    // W_N^{(256 c + t) ko}: the columns of outer stage 0 (a = c)
 #pragma unroll
-        for (int k = 1; k < 16; k++) twO[k - 1] = twbig[(tid * k) & (kBig - 1)];
+        for (int j = 0; j < 16; j++)
+            if (j % M != 0) twO[j] = twbig[((256 * (j / M) + tid) * (j % M)) & (kBig - 1)];
     };
     reload_twO();
 
@@ -318,7 +353,7 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
 #pragma unroll
         for (int k = 0; k < 16; k++) z[k] = 0.0f;
 #pragma unroll 1
-        for (int ko = 0; ko < 16; ko++) tmem_st16(tm_acc + ko * 16, z);
+        for (int ko = 0; ko < M; ko++) tmem_st16(tm_acc + ko * 16, z);
         tmem_st_wait();
     }
 
@@ -329,7 +364,7 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
 #define RPF_SOLO_STG(p, v) stg_c32((p), (v))
 #endif
     uint8_t *sbase = reinterpret_cast<uint8_t *>(scratch + (size_t)blockIdx.x * kBig + tid);   // my column of every block
-    const uint32_t raw_ld = sm + kOffRaw + 2 * tid;              // + slot * 16 KiB + half * 512 + n1 * 1024
+    const uint32_t raw_ld = sm + kOffRaw + 2 * tid;              // + slot * 16 KiB + half * C * 512 + c * 512 + n1 * kChunk
     const uint32_t row_ld = sm + kOffRow + tid * 8;              // + s * 32 KiB + a * 2048: x[256 a + t]
     const uint32_t s1_st = sm + kOffS1 + tid * 128 + ((tid & 7) << 4);
     const uint32_t s1_ld = sm + kOffS1 + hi * 128 + ((((lo >> 1) ^ (hi & 7)) << 4) | ((lo & 1) << 3));   // + n2 * 2048
@@ -343,7 +378,7 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
 #pragma unroll
         for (int k = 0; k < 16; k++) z[k] = 0.0f;
 #pragma unroll 1
-        for (int ko = 0; ko < 16; ko++) {
+        for (int ko = 0; ko < M; ko++) {
             float a16[16];
             tmem_ld16(tm_acc + ko * 16, a16);
             double cur[16];
@@ -386,55 +421,69 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         fetch();
     };
     float win[WINDOW ? 16 : 1];
-    auto load_window = [&](int a) {                  // w[4096 n1 + 256 a + t]
+    auto load_window = [&](int o) {                  // outer stage o: win[c M + n1] = w[4096 n1 + 256 (o C + c) + t]
         if (WINDOW) {
 #pragma unroll
-            for (int n1 = 0; n1 < 16; n1++) win[n1] = __ldg(window + n1 * kN + a * 256 + tid);
+            for (int j = 0; j < 16; j++) win[j] = __ldg(window + (j % M) * kN + (o * C + j / M) * 256 + tid);
         }
     };
     // raw bytes of pair p, outer stage `half` of it -> raw[]
     auto fetch_raw = [&](int p, int half) {
         const int slot = p & (kRawStg - 1);
         if (half == 0) mbar_wait(sm + 8 * bar_full(slot), (uint32_t)((p / kRawStg) & 1));
-        lds16x16<kPairChunk>(raw_ld + slot * kRawSlot + half * 512, raw);
+        lds16x16<M, kChunk>(raw_ld + slot * kRawSlot + half * (C * 512), raw);
     };
-    // Outer stage a of a spectrum stored with parity `par`: raw[] holds x[4096 n1 + 256 a + t].  Radix-16 over n1 on the
-    // biased bytes (exact, as in pass 1 of pipe4096.cu), times W_65536^{(256 a + t) ko}, 16 stores into my column of the
-    // blocks (ko, a); then the twiddles move on to a + 1.
-    auto outer = [&](c32 (&v)[16], int a, int par, auto &&fetch) {
+    // Outer stage o = 2 i + half of a spectrum stored with layout `par`: raw[c M + n1] holds x[4096 n1 + 256 a + t] for my
+    // C columns a = o C + c.  Radix-M over n1 on the biased bytes (exact, as in pass 1 of pipe4096.cu), times
+    // W_N^{(256 a + t) ko}, 16 stores into my element of the blocks (ko, a); then the twiddles move on by C values of a.
+    auto outer = [&](c32 (&v)[16], int i, int half, int par, auto &&fetch) {
 #pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) {
-            v[n1] = unpack_biased(raw[n1]);
-            if (WINDOW) v[n1] = __fadd2_rn(v[n1], make_float2(-kBias, -kBias));   // byte - 127.0f, exact
+        for (int j = 0; j < 16; j++) {
+            v[j] = unpack_biased(raw[j]);
+            if (WINDOW) v[j] = __fadd2_rn(v[j], make_float2(-kBias, -kBias));     // byte - 127.0f, exact
+            if (WINDOW && M < 16) v[j] = __fmul2_rn(v[j], make_float2(win[j], win[j]));
         }
-        c32 y[16];
-        if (WINDOW) dft16_first_windowed(v, win); else dft16_first(v);
-        // blocks [ko][a] (parity 0) or [a][ko] (parity 1)
-        uint8_t *p = sbase + (par == 0 ? a * kBlk : a * (16 * kBlk));
-        // the 16 stores leave in four groups, each behind the radix-4 that produces its outputs ko = q + 4 k1: sixteen
-        // back to back fill the LSU queue, and whatever next overwrites one of their registers waits for it to drain
-        auto emit = [&](auto qc) {
-            constexpr int q = decltype(qc)::value;
-#pragma unroll
-            for (int k1 = 0; k1 < 4; k1++) {
-                const int ko = q + 4 * k1;
-                c32 o = y[ko];
-                if (!WINDOW && ko == 0) o = __fadd2_rn(o, make_float2(-16.0f * kBias, -16.0f * kBias));   // the bias survives in ko = 0 only (exact)
-                if (ko != 0) o = cmul(o, twO[ko - 1]);
-                if (par == 0) RPF_SOLO_STG(p + ko * (16 * kBlk), o); else RPF_SOLO_STG(p + ko * kBlk, o);
-                if (ko != 0) twO[ko - 1] = cmul(twO[ko - 1], w256_re(ko), w256_im(ko));
-            }
+        // my element of block (ko, a): layout 0 = blk0, layout 1 = blk1 (Geo<M>); the part that depends on (i, half) here,
+        // the part that depends on (c, ko) as an immediate below
+        uint8_t *p = sbase + (size_t)(par == 0 ? i * AL + half * C : G::f1(i * AL + half * C)) * kBlk;   // (a = i AL + half C + c)
+        auto put = [&](int c, int ko, c32 o) {       // (c, ko: compile-time after unrolling)
+            if (!WINDOW && ko == 0) o = __fadd2_rn(o, make_float2(-(float)M * kBias, -(float)M * kBias));   // the bias survives in ko = 0 only (exact)
+            if (ko != 0) o = cmul(o, twO[c * M + ko]);
+            if (par == 0) RPF_SOLO_STG(p + (ko * 16 + c) * kBlk, o);
+            else RPF_SOLO_STG(p + (G::g1(ko) + G::f1(c)) * kBlk, o);
+            if (ko != 0) twO[c * M + ko] = cmul(twO[c * M + ko], w256_re(ko * (256 / (M * M))), w256_im(ko * (256 / (M * M))));
         };
-        radix4_tw<0>(v[0], v[1], v[2], v[3], y[0], y[4], y[8], y[12]);
-        emit(std::integral_constant<int, 0>());
-        radix4_tw<1>(v[4], v[5], v[6], v[7], y[1], y[5], y[9], y[13]);
-        emit(std::integral_constant<int, 1>());
-        fetch();
-        if (WINDOW) load_window((a + 1) & 15);                                   // for the next outer stage
-        radix4_tw<2>(v[8], v[9], v[10], v[11], y[2], y[6], y[10], y[14]);
-        emit(std::integral_constant<int, 2>());
-        radix4_tw<3>(v[12], v[13], v[14], v[15], y[3], y[7], y[11], y[15]);
-        emit(std::integral_constant<int, 3>());
+        if (M == 16) {
+            c32 y[16];
+            if (WINDOW) dft16_first_windowed(v, win); else dft16_first(v);
+            // the 16 stores leave in four groups, each behind the radix-4 that produces its outputs ko = q + 4 k1: sixteen
+            // back to back fill the LSU queue, and whatever next overwrites one of their registers waits for it to drain
+            radix4_tw<0>(v[0], v[1], v[2], v[3], y[0], y[4], y[8], y[12]);
+#pragma unroll
+            for (int k1 = 0; k1 < 4; k1++) put(0, 4 * k1, y[4 * k1]);
+            radix4_tw<1>(v[4], v[5], v[6], v[7], y[1], y[5], y[9], y[13]);
+#pragma unroll
+            for (int k1 = 0; k1 < 4; k1++) put(0, 1 + 4 * k1, y[1 + 4 * k1]);
+            fetch();
+            if (WINDOW) load_window((2 * i + half + 1) & (M - 1));               // for the next outer stage
+            radix4_tw<2>(v[8], v[9], v[10], v[11], y[2], y[6], y[10], y[14]);
+#pragma unroll
+            for (int k1 = 0; k1 < 4; k1++) put(0, 2 + 4 * k1, y[2 + 4 * k1]);
+            radix4_tw<3>(v[12], v[13], v[14], v[15], y[3], y[7], y[11], y[15]);
+#pragma unroll
+            for (int k1 = 0; k1 < 4; k1++) put(0, 3 + 4 * k1, y[3 + 4 * k1]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                Dft<M>::run(&v[c * M]);
+#pragma unroll
+                for (int ko = 0; ko < M; ko++) put(c, ko, v[c * M + ko]);
+                if (c == C / 2 - 1) {
+                    fetch();
+                    if (WINDOW) load_window((2 * i + half + 1) & (M - 1));
+                }
+            }
+        }
     };
     // my 16 inputs x[256 a + t] of stream s of iteration g, staged by the helper warps -> registers
     auto load_row = [&](c32 (&v)[16], int s, int g) {
@@ -446,11 +495,11 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
     load_window(0);
     fetch_raw(0, 0);
 #pragma unroll 1
-    for (int pp = 0; pp < 8; pp++) {
-        outer(vB, 2 * pp, 0, [&]() { fetch_raw(pp, 1); });
-        outer(vB, 2 * pp + 1, 0, [&]() {});
+    for (int pp = 0; pp < IPS; pp++) {
+        outer(vB, pp, 0, 0, [&]() { fetch_raw(pp, 1); });
+        outer(vB, pp, 1, 0, [&]() {});
         warp_arrive(sm + 8 * bar_empty(pp & (kRawStg - 1)));
-        if (pp < 7) fetch_raw(pp + 1, 0);
+        if (pp < IPS - 1) fetch_raw(pp + 1, 0);
     }
     warp_arrive(sm + 8 * kBarWritten);
     load_row(vA, 0, 0);
@@ -459,8 +508,8 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
     int since_flush = 0;
     for (int j = 0; j < nit; j++) {
         const uint32_t ph = (uint32_t)(j & 1);
-        const int i = j & 7;                              // streams A, B = outer bins 2i, 2i + 1 of spectrum j >> 3
-        const int par = (j >> 3) & 1;
+        const int i = j % IPS;                            // streams A, B = outer bins 2i, 2i + 1 of spectrum j / IPS
+        const int par = (j / IPS) & 1;
         if (i == 0) { reload_twO(); load_window(0); }     // the outer stages of this spectrum's successor start at a = 0
 
         // ---- (A,1) | row B ------------------------------------------------------------------------
@@ -474,12 +523,12 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         post2(vA, 0, []() {});
         // ---- (B,2) | S2[A]; raw bytes of the first outer stage ---------------------------------------
         radix(vB, [&]() { mbar_wait(rd + 8, ph); lds64x16<128>(s2_ld, vA); });
-        post2(vB, 1, [&]() { fetch_raw(8 + j, 0); });
-        // ---- O(2i), O(2i + 1) of the next spectrum (parity par ^ 1) ---------------------------------
-        outer(vB, 2 * i, par ^ 1, [&]() { fetch_raw(8 + j, 1); });
-        outer(vB, 2 * i + 1, par ^ 1, [&]() {});
-        warp_arrive(sm + 8 * bar_empty(j & (kRawStg - 1)));
-        if (i == 7) warp_arrive(sm + 8 * kBarWritten);    // the outer pass of the next spectrum is complete
+        post2(vB, 1, [&]() { fetch_raw(IPS + j, 0); });
+        // ---- O(2i), O(2i + 1) of the next spectrum (layout par ^ 1) ---------------------------------
+        outer(vB, i, 0, par ^ 1, [&]() { fetch_raw(IPS + j, 1); });
+        outer(vB, i, 1, par ^ 1, [&]() {});
+        warp_arrive(sm + 8 * bar_empty((IPS + j) & (kRawStg - 1)));
+        if (i == IPS - 1) warp_arrive(sm + 8 * kBarWritten);   // the outer pass of the next spectrum is complete
         // ---- (A,3) | S2[B] ------------------------------------------------------------------------
         tmem_st_wait();                                   // (the stores of the previous iteration: long done)
         tmem_ld16(tm_acc + (2 * i) * 16, acc);
@@ -494,7 +543,7 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         power(vB);
         tmem_st16(tm_acc + (2 * i + 1) * 16, acc);
 
-        if (i == 7 && ++since_flush == kFlushSpectra) { tmem_st_wait(); flush(); since_flush = 0; }
+        if (i == IPS - 1 && ++since_flush == kFlushSpectra) { tmem_st_wait(); flush(); since_flush = 0; }
     }
     tmem_st_wait();
     flush();
@@ -527,9 +576,15 @@ cudaError_t rpf_solo65536_configure(size_t *saved_limit)
         cudaGetLastError();                        // best effort: without the set-aside the hints alone still work
     }
 #endif
-    cudaError_t e = cudaFuncSetAttribute(solo65536_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(solo65536_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    const void *fns[] = {(const void *)solo65536_kernel<false, 2>, (const void *)solo65536_kernel<true, 2>,
+                         (const void *)solo65536_kernel<false, 4>, (const void *)solo65536_kernel<true, 4>,
+                         (const void *)solo65536_kernel<false, 8>, (const void *)solo65536_kernel<true, 8>,
+                         (const void *)solo65536_kernel<false, 16>, (const void *)solo65536_kernel<true, 16>};
+    for (const void *f : fns) {
+        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 void rpf_solo65536_release(size_t saved_limit)
@@ -540,16 +595,28 @@ void rpf_solo65536_release(size_t saved_limit)
     }
 }
 
-size_t rpf_solo65536_scratch_bytes(int grid) { return (size_t)grid * kBig * sizeof(float2); }
+size_t rpf_solo65536_scratch_bytes(int M, int grid) { return (size_t)grid * M * kN * sizeof(float2); }
 
-// L.grid = CTAs (<= SMs), L.rows = 16 rows of 4096 doubles per CTA, scratch = rpf_solo65536_scratch_bytes(L.grid).
+template <int M>
+static cudaError_t launch_solo(const RpfLaunch &L, const float2 *twbig, float2 *scratch)
+{
+    const unsigned grid = (unsigned)((int64_t)L.grid < L.nspec ? L.grid : L.nspec);
+    if (L.window)
+        solo65536_kernel<true, M><<<grid, kLaunchThreads, kSmem, L.stream>>>(L.bytes, L.nspec, L.twiddle, twbig, L.window, scratch, L.rows);
+    else
+        solo65536_kernel<false, M><<<grid, kLaunchThreads, kSmem, L.stream>>>(L.bytes, L.nspec, L.twiddle, twbig, nullptr, scratch, L.rows);
+    return cudaGetLastError();
+}
+
+// L.M = outer radix, L.grid = CTAs (<= SMs), L.rows = M rows of 4096 doubles per CTA, scratch = rpf_solo65536_scratch_bytes(M, L.grid).
 cudaError_t rpf_launch_solo65536(const RpfLaunch &L, const float2 *twbig, float2 *scratch)
 {
     if (L.nspec <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((int64_t)L.grid < L.nspec ? L.grid : L.nspec);
-    if (L.window)
-        solo65536_kernel<true><<<grid, kLaunchThreads, kSmem, L.stream>>>(L.bytes, L.nspec, L.twiddle, twbig, L.window, scratch, L.rows);
-    else
-        solo65536_kernel<false><<<grid, kLaunchThreads, kSmem, L.stream>>>(L.bytes, L.nspec, L.twiddle, twbig, nullptr, scratch, L.rows);
-    return cudaGetLastError();
+    switch (L.M) {
+        case 2: return launch_solo<2>(L, twbig, scratch);
+        case 4: return launch_solo<4>(L, twbig, scratch);
+        case 8: return launch_solo<8>(L, twbig, scratch);
+        case 16: return launch_solo<16>(L, twbig, scratch);
+        default: return cudaErrorInvalidValue;
+    }
 }

@@ -593,6 +593,32 @@ def test_solo65536_window(R):
         assert relmax(ps, po) < TOL
 
 
+@pytest.mark.parametrize("N", [8192, 16384, 32768])
+@pytest.mark.parametrize("R", [1, 3, 9, 148, 149, 300, 1000])
+@pytest.mark.parametrize("windowed", [False, True])
+def test_solo_kernel_other_outer_radices(N, R, windowed):
+    """The one-CTA-per-spectrum kernel with outer radix 2, 4, 8 (an outer stage = 8 / 4 / 2 radix-M butterflies, 1 / 2 / 4
+    iterations per spectrum, in-place scratch of M x 16 blocks with the two layouts of Geo<M>): against the two-kernel
+    path, the oracle for small counts, Parseval."""
+    if windowed and R not in (3, 149, 300):
+        pytest.skip("window: three counts")
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32) if windowed else None
+    s = stream(2 * N * R, seed=R * 19 + N, mode=1)
+    with Context(N, flags=pkg.capi.RPF_FLAG_SOLO65536) as c:
+        assert c.plan_name == "solo"
+    ps, done = run_gpu(N, R, [s], window=w, flags=pkg.capi.RPF_FLAG_SOLO65536)
+    pt, done_t = run_gpu(N, R, [s], window=w, flags=pkg.capi.RPF_FLAG_FOURSTEP)
+    assert done == done_t == R
+    assert relmax(ps, pt) < 2e-6 and perbin(ps, pt) < (2e-5 if R >= 9 else 1e-3)
+    if R <= 9:
+        po, _ = ol.oracle_run_stream(N, R, s, window=w, buf_length=s.size)
+        assert relmax(ps, po) < TOL
+        assert perbin(ps, po) < (TOL if R >= 9 else 1e-3)
+    if not windowed:
+        x = s.astype(np.int64) - 127
+        assert ps.sum() == pytest.approx(N * float((x * x).sum()), rel=1e-6)
+
+
 def test_solo65536_kats_pushes_and_reuse():
     """The one-CTA-per-spectrum kernel on known answers (zero input, DC, a tone: bin exact), over several pushes that
     straddle spectra, and reused after rpf_reset (tensor-memory accumulators and float64 rows start from zero)."""
