@@ -99,11 +99,11 @@ typedef struct rpf_config {
  * handed to the inner 4096-point pipelines through distributed shared memory (st.async + remote mbarriers) instead of
  * a complex64 scratch in HBM.  Same results; measured slower than the default two-kernel path. */
 #define RPF_FLAG_CLUSTER65536 16u
-/* N = 65536, kernel choice (A/B comparisons; default: SOLO65536 for launches of at least 96 spectra, the two-kernel
- * four-step path for shorter ones -- both add into the same private accumulator rows):
- *   RPF_FLAG_SOLO65536  every launch in one kernel, one CTA per spectrum: the outer radix-16 is handed to the 16 inner
- *                       4096-point transforms thread-privately through a 512 KiB per-CTA scratch that stays in L2, the
- *                       65536 accumulators of a CTA live in tensor memory (csrc/solo65536.cu).  While
+/* N = 8192 ... 65536 (N = M * 4096), kernel choice (A/B comparisons; default: SOLO65536 for launches of at least 96
+ * spectra, the two-kernel four-step path for shorter ones -- both add into the same private accumulator rows):
+ *   RPF_FLAG_SOLO65536  every launch in one kernel, one CTA per spectrum: the outer radix-M is handed to the M inner
+ *                       4096-point transforms thread-privately through a 32 M KiB per-CTA scratch that stays in L2, the
+ *                       N accumulators of a CTA live in tensor memory (csrc/solo65536.cu).  While
  *                       such a context exists the device's persisting-L2 set-aside is raised to its maximum.
  *   RPF_FLAG_FOURSTEP   every launch on the two-kernel path (outer radix-16 into a complex64 scratch in HBM, 4096-point
  *                       transforms of its rows). */
