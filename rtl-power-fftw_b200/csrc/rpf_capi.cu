@@ -406,8 +406,8 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
                 if (ncl * 16 > d.grid) ncl = d.grid / 16;          // (rows are sized by d.grid)
                 d.cluster_grid = ncl * 16;
             }
-            // 65536 bins: one launch, one CTA per spectrum (solo65536.cu): 379 against 299 Gsamples/s for the two-kernel
-            // path on long launches.  A launch costs every CTA the time of a whole spectrum (~30 us) however few spectra
+            // 8192 ... 65536 bins: one launch, one CTA per spectrum (solo65536.cu): 375-383 against 299-309 Gsamples/s for
+            // the two-kernel path on long launches.  A launch costs every CTA the time of a whole spectrum (~30 us) however few spectra
             // there are, so short ones (the reference's 1,638,400-byte reads hold 12.5 spectra) stay on the two-kernel
             // path; both add into the same private rows (row index mod 16 = outer bin on either path).
             const uint32_t forced = cfg->flags & (RPF_FLAG_SOLO65536 | RPF_FLAG_FOURSTEP | RPF_FLAG_CLUSTER65536 | RPF_FLAG_LOCKSTEP);

@@ -73,6 +73,14 @@ struct Geo {
     static __host__ __device__ constexpr int blk0(int ko, int a) { return ko * 16 + a; }
     static __host__ __device__ constexpr int g1(int ko) { return kT16 ? ko : (ko & 1) * 16 + (ko >> 1) * AL; }
     static __host__ __device__ constexpr int f1(int a) { return kT16 ? a * 16 : (a / AL) * 32 + (a % AL); }
+    // M <= 4: the hand-off (16 M complex values per thread) fits tensor memory next to the accumulators -- no scratch, no
+    // helper warps, no L2 traffic.  Cell (ko, a) = two 32-bit columns at kTmHand + 2 * blk(ko, a); M = 2 keeps layout 0
+    // for every spectrum (its single iteration consumes both rows before its outer stages produce anything).
+#ifndef RPF_SOLO_TMEM_HANDOFF
+#define RPF_SOLO_TMEM_HANDOFF 1
+#endif
+    static constexpr bool kTm = RPF_SOLO_TMEM_HANDOFF && M <= 4;
+    static constexpr int kTmHand = 64;            // first hand-off column (accumulators: columns [0, 16 M))
     static constexpr int kRun = kT16 ? 1 : AL;    // layout 1: a row is runs of kRun blocks ...
     static constexpr int kRunStride1 = kT16 ? 16 : 32;   // ... this many blocks apart (layout 0: contiguous)
 };
@@ -216,6 +224,40 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16])
         ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),
           "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]) : "memory");
 }
+// 2 N consecutive columns <-> N complex values
+__device__ __forceinline__ void tmem_ld_c16(uint32_t taddr, c32 *v)       // 32 columns
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
+          "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y),
+          "=f"(v[8].x), "=f"(v[8].y), "=f"(v[9].x), "=f"(v[9].y), "=f"(v[10].x), "=f"(v[10].y), "=f"(v[11].x), "=f"(v[11].y),
+          "=f"(v[12].x), "=f"(v[12].y), "=f"(v[13].x), "=f"(v[13].y), "=f"(v[14].x), "=f"(v[14].y), "=f"(v[15].x), "=f"(v[15].y)
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_c8(uint32_t taddr, c32 *v)        // 16 columns
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
+          "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y)
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_c8(uint32_t taddr, const c32 *v)  // 16 columns
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y),
+          "f"(v[4].x), "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y) : "memory");
+}
+__device__ __forceinline__ void tmem_st_c4(uint32_t taddr, const c32 *v)  // 8 columns
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -267,7 +309,7 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
 
     if (tid >= kThreads) {                             // the copy warp group
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (tid >= kThreads + 32 && tid < kThreads + 32 + kHelpers) {
+        if (!G::kTm && tid >= kThreads + 32 && tid < kThreads + 32 + kHelpers) {
             // Row staging: generation g = the rows ko = 2i, 2i + 1 (i = g % IPS) of my spectrum number g / IPS, wanted by
             // iteration g.  A row is fetched as soon as its slot has been read for generation g - 1 (a whole iteration
             // before it is needed); only the first two rows of a spectrum also have to wait for the last outer stages of
@@ -348,6 +390,8 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
 
     // my accumulators: lanes of my warp's quadrant, columns [256 (warp >> 2), +256): column 16 ko + k3
     const uint32_t tm_acc = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) * 256);
+    const uint32_t tm_hand = tm_acc + G::kTmHand;                // (M <= 4) my cells of the hand-off
+    (void)tm_hand;
     {
         float z[16];
 #pragma unroll
@@ -472,7 +516,7 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
             radix4_tw<3>(v[12], v[13], v[14], v[15], y[3], y[7], y[11], y[15]);
 #pragma unroll
             for (int k1 = 0; k1 < 4; k1++) put(0, 3 + 4 * k1, y[3 + 4 * k1]);
-        } else {
+        } else if (!G::kTm) {
 #pragma unroll
             for (int c = 0; c < C; c++) {
                 Dft<M>::run(&v[c * M]);
@@ -483,12 +527,50 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
                     if (WINDOW) load_window((2 * i + half + 1) & (M - 1));
                 }
             }
+        } else {
+            // hand-off through tensor memory: per ko the C values of this stage are C consecutive cells
+            c32 o[M][C];
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                Dft<M>::run(&v[c * M]);
+#pragma unroll
+                for (int ko = 0; ko < M; ko++) {
+                    c32 x = v[c * M + ko];
+                    if (!WINDOW && ko == 0) x = __fadd2_rn(x, make_float2(-(float)M * kBias, -(float)M * kBias));
+                    if (ko != 0) {
+                        x = cmul(x, twO[c * M + ko]);
+                        twO[c * M + ko] = cmul(twO[c * M + ko], w256_re(ko * (256 / (M * M))), w256_im(ko * (256 / (M * M))));
+                    }
+                    o[ko][c] = x;
+                }
+                if (c == C / 2 - 1) {
+                    fetch();
+                    if (WINDOW) load_window((2 * i + half + 1) & (M - 1));
+                }
+            }
+            const bool l1 = M == 4 && par != 0;
+            const uint32_t cell0 = l1 ? (uint32_t)G::f1(i * AL + half * C) : (uint32_t)(i * AL + half * C);
+#pragma unroll
+            for (int ko = 0; ko < M; ko++) {
+                const uint32_t t = tm_hand + 2 * (cell0 + (l1 ? G::g1(ko) : ko * 16));
+                if (C == 8) tmem_st_c8(t, o[ko]); else tmem_st_c4(t, o[ko]);
+            }
         }
     };
     // my 16 inputs x[256 a + t] of stream s of iteration g, staged by the helper warps -> registers
     auto load_row = [&](c32 (&v)[16], int s, int g) {
-        mbar_wait(sm + 8 * bar_rowfull(s), (uint32_t)(g & 1));
-        lds64x16<2048>(row_ld + s * kStreamS, v);
+        if (G::kTm) {
+            const int gi = g % IPS, ko = 2 * gi + s;
+            if (M == 2 || ((g / IPS) & 1) == 0) {
+                tmem_ld_c16(tm_hand + 2 * (ko * 16), v);                       // layout 0: 16 consecutive cells
+            } else {
+                tmem_ld_c8(tm_hand + 2 * G::g1(ko), v);                       // layout 1: two runs of 8 cells, 32 apart
+                tmem_ld_c8(tm_hand + 2 * (G::g1(ko) + 32), v + 8);
+            }
+        } else {
+            mbar_wait(sm + 8 * bar_rowfull(s), (uint32_t)(g & 1));
+            lds64x16<2048>(row_ld + s * kStreamS, v);
+        }
     };
 
     // ---- prologue: the whole outer pass of my first spectrum; rows 0 and 1 on their way ------------------------
@@ -501,7 +583,7 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         warp_arrive(sm + 8 * bar_empty(pp & (kRawStg - 1)));
         if (pp < IPS - 1) fetch_raw(pp + 1, 0);
     }
-    warp_arrive(sm + 8 * kBarWritten);
+    if (G::kTm) tmem_st_wait(); else warp_arrive(sm + 8 * kBarWritten);
     load_row(vA, 0, 0);
 
     const uint32_t rd = sm + 8 * bar_rd(0, 1);           // bar_rd(s, e) = rd + 8 (2 s + e - 1)
@@ -513,10 +595,12 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         if (i == 0) { reload_twO(); load_window(0); }     // the outer stages of this spectrum's successor start at a = 0
 
         // ---- (A,1) | row B ------------------------------------------------------------------------
-        radix(vA, [&]() { warp_arrive(sm + 8 * bar_rowfree(0)); load_row(vB, 1, j); });     // (row A has been consumed)
+        if (G::kTm) tmem_ld_wait();                       // row A (tcgen05.ld in (B,3) of the previous iteration)
+        radix(vA, [&]() { if (!G::kTm) warp_arrive(sm + 8 * bar_rowfree(0)); load_row(vB, 1, j); });     // (row A has been consumed)
         post1(vA, 0);
         // ---- (B,1) | S1[A] ------------------------------------------------------------------------
-        radix(vB, [&]() { warp_arrive(sm + 8 * bar_rowfree(1)); mbar_wait(rd, ph); lds64x16<2048>(s1_ld, vA); });
+        if (G::kTm) tmem_ld_wait();                       // row B
+        radix(vB, [&]() { if (!G::kTm) warp_arrive(sm + 8 * bar_rowfree(1)); mbar_wait(rd, ph); lds64x16<2048>(s1_ld, vA); });
         post1(vB, 1);
         // ---- (A,2) | S1[B] ------------------------------------------------------------------------
         radix(vA, [&]() { mbar_wait(rd + 16, ph); lds64x16<2048>(s1_ld + kStreamS, vB); });
@@ -528,7 +612,7 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
         outer(vB, i, 0, par ^ 1, [&]() { fetch_raw(IPS + j, 1); });
         outer(vB, i, 1, par ^ 1, [&]() {});
         warp_arrive(sm + 8 * bar_empty((IPS + j) & (kRawStg - 1)));
-        if (i == IPS - 1) warp_arrive(sm + 8 * kBarWritten);   // the outer pass of the next spectrum is complete
+        if (!G::kTm && i == IPS - 1) warp_arrive(sm + 8 * kBarWritten);   // the outer pass of the next spectrum is complete
         // ---- (A,3) | S2[B] ------------------------------------------------------------------------
         tmem_st_wait();                                   // (the stores of the previous iteration: long done)
         tmem_ld16(tm_acc + (2 * i) * 16, acc);

@@ -619,6 +619,30 @@ def test_solo_kernel_other_outer_radices(N, R, windowed):
         assert ps.sum() == pytest.approx(N * float((x * x).sum()), rel=1e-6)
 
 
+@pytest.mark.parametrize("N", [8192, 32768, 65536])
+def test_solo_kernel_long_launch_flushes_tensor_memory(N):
+    """A launch long enough for every CTA to flush its tensor-memory accumulators inside the loop (every 128 spectra
+    per CTA): 148 x 128 + 3000 spectra, device-resident.  Exact Parseval over the whole stream, the two-kernel path on
+    the same bytes, linearity (the stream is a block repeated, so pwr == copies x pwr(block) to float32-grouping
+    accuracy)."""
+    import torch
+    P = 148 * 8 + 17                                   # block: every CTA gets 8 or 9 spectra
+    copies = 17                                        # 20,417 spectra: 137-138 per CTA
+    block = pkg.synth_fill_host(2 * N * P, 0, seed=N + 77, mode=1)
+    dev = torch.from_numpy(block).cuda().repeat(copies)
+    torch.cuda.synchronize()
+    with Context(N, flags=pkg.capi.RPF_FLAG_SOLO65536) as c:
+        c.reset(P); c.push_device(dev.data_ptr(), 2 * N * P); p1, d1 = c.finish()
+        c.reset(P * copies); c.push_device(dev.data_ptr(), dev.numel()); pc, dc = c.finish()
+    with Context(N, flags=pkg.capi.RPF_FLAG_FOURSTEP) as c:
+        c.reset(P * copies); c.push_device(dev.data_ptr(), dev.numel()); pt, dt = c.finish()
+    assert d1 == P and dc == dt == P * copies
+    x = block.astype(np.int64) - 127
+    assert pc.sum() == pytest.approx(copies * N * float((x * x).sum()), rel=1e-6)
+    assert relmax(pc, copies * p1) < 2e-6 and perbin(pc, copies * p1) < 2e-5
+    assert relmax(pc, pt) < 2e-6 and perbin(pc, pt) < 2e-5
+
+
 def test_solo65536_kats_pushes_and_reuse():
     """The one-CTA-per-spectrum kernel on known answers (zero input, DC, a tone: bin exact), over several pushes that
     straddle spectra, and reused after rpf_reset (tensor-memory accumulators and float64 rows start from zero)."""
