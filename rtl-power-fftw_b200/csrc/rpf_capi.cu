@@ -412,13 +412,15 @@ int create_device(rpf_ctx *c, rpf_dev &d, const rpf_config *cfg)
             // path; both add into the same private rows (row index mod 16 = outer bin on either path).
             const uint32_t forced = cfg->flags & (RPF_FLAG_SOLO65536 | RPF_FLAG_FOURSTEP | RPF_FLAG_CLUSTER65536 | RPF_FLAG_LOCKSTEP);
             if (forced ? (forced & RPF_FLAG_SOLO65536) != 0 : cfg->scratch_mib == 0) {
-                CU(c, rpf_solo65536_configure(&d.solo_saved_l2));
+                CU(c, rpf_solo65536_configure(c->M, &d.solo_saved_l2));
                 d.solo_grid = sms;
                 d.solo_min = (cfg->flags & RPF_FLAG_SOLO65536) ? 1 : 96;
                 // with the flag, rpf_config.scratch_mib bounds the scratch (32 M KiB per CTA) and so the CTA count (tuning runs)
                 if (forced && cfg->scratch_mib > 0 && cfg->scratch_mib * (32 / c->M) < d.solo_grid) d.solo_grid = cfg->scratch_mib * (32 / c->M);
-                CU(c, cudaMalloc(&d.d_solo, rpf_solo65536_scratch_bytes(c->M, d.solo_grid)));
-                CU(c, cudaMemset(d.d_solo, 0, rpf_solo65536_scratch_bytes(c->M, d.solo_grid)));
+                if (const size_t sb = rpf_solo65536_scratch_bytes(c->M, d.solo_grid)) {      // (0: hand-off through tensor memory)
+                    CU(c, cudaMalloc(&d.d_solo, sb));
+                    CU(c, cudaMemset(d.d_solo, 0, sb));
+                }
                 d.cluster_grid = 0;
             }
             break;

@@ -46,7 +46,7 @@ cudaError_t rpf_launch_cluster65536(const RpfLaunch &L, const float2 *twiddle_bi
 // N = M * 4096 (M = 2 ... 16) in one launch, one CTA per spectrum: thread-private hand-off of the outer radix-M through an
 // L2-resident scratch (rpf_solo65536_scratch_bytes(M, grid) bytes), accumulators in tensor memory.  L.M = M, L.grid = CTAs,
 // L.rows = M rows of 4096 doubles per CTA (row M c + ko).
-cudaError_t rpf_solo65536_configure(size_t *saved_persisting_l2_limit);   // raises the device's persisting-L2 set-aside
+cudaError_t rpf_solo65536_configure(int M, size_t *saved_persisting_l2_limit);   // M >= 8: raises the device's persisting-L2 set-aside
 void rpf_solo65536_release(size_t saved_persisting_l2_limit);              // ... and puts it back
 size_t rpf_solo65536_scratch_bytes(int M, int grid);
 cudaError_t rpf_launch_solo65536(const RpfLaunch &L, const float2 *twiddle_big, float2 *scratch);

@@ -24,6 +24,9 @@
 //   * a CTA that runs all 16 inner transforms needs 16 x 16 accumulators per thread: they live in TENSOR MEMORY used
 //     as a per-thread scratchpad (256 KiB = 256 floats per thread: tcgen05.ld.x16, 32 FFMA, tcgen05.st.x16 per inner
 //     transform), flushed to the CTA's float64 rows every 128 spectra like everywhere else;
+//   * M <= 4 (8192 / 16384 bins): the hand-off itself fits tensor memory (16 M complex values per thread next to the
+//     16 M accumulators): tcgen05.st from the outer stage, one tcgen05.ld.x32 (or two .x16) per row -- no scratch, no
+//     helper warps, no barrier for the hand-off, no L2 traffic beyond the raw bytes (602 / 534 Gsamples/s);
 //   * the twiddle W_65536^{(256 a + t) ko} of the outer pass is kept in registers and advanced from a to a + 1 by a
 //     multiplication with the compile-time constant W_256^{ko}, reloaded exactly at a = 0 of every spectrum.
 //
@@ -645,11 +648,11 @@ solo65536_kernel(const uint8_t *__restrict__ bytes, int64_t nspec, const float2 
 #ifndef RPF_SOLO_PERSIST
 #define RPF_SOLO_PERSIST 1
 #endif
-cudaError_t rpf_solo65536_configure(size_t *saved_limit)
+cudaError_t rpf_solo65536_configure(int M, size_t *saved_limit)
 {
     *saved_limit = (size_t)-1;
 #if RPF_SOLO_PERSIST
-    {
+    if (!Geo<2>::kTm || M > 4) {               // (M <= 4 hands over through tensor memory: nothing to keep in L2)
         int dev = 0, maxp = 0;
         size_t cur = 0;
         if (cudaGetDevice(&dev) == cudaSuccess &&
@@ -679,7 +682,11 @@ void rpf_solo65536_release(size_t saved_limit)
     }
 }
 
-size_t rpf_solo65536_scratch_bytes(int M, int grid) { return (size_t)grid * M * kN * sizeof(float2); }
+size_t rpf_solo65536_scratch_bytes(int M, int grid)
+{
+    if (Geo<2>::kTm && M <= 4) return 0;       // hand-off through tensor memory
+    return (size_t)grid * M * kN * sizeof(float2);
+}
 
 template <int M>
 static cudaError_t launch_solo(const RpfLaunch &L, const float2 *twbig, float2 *scratch)
