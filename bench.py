@@ -235,7 +235,7 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     ring = numpy_stream(1638400 * 8)
     if not ol.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (reference sources absent)"}))
+        emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (reference sources absent)"}))
         return
     reps = calibrate_reps(cores, ring, 1.5)      # a step = ~1.5 s of wall clock
     for _ in range(args.warmup):
@@ -258,7 +258,7 @@ def run_reference_arm(args):
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def workload_config(n_gpus):
@@ -411,6 +411,16 @@ def check_parity(pkg, torch, dist, stream_dev, pwr_dev, pw, nspec, nbytes, cur, 
     return parity
 
 
+_OUT = None
+
+
+def emit(text):
+    """The one JSON line, on the process's real stdout."""
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -424,6 +434,12 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help=argparse.SUPPRESS)   # ncu launch lists: only the step's kernels
     ap.add_argument("--flags", type=int, default=0, help=argparse.SUPPRESS)   # rpf_config.flags of the timed context
     args = ap.parse_args()
+    # The JSON line must be the ONLY thing on stdout: libraries chat there (NCCL prints a version banner when torch
+    # creates its communicator under NCCL_DEBUG).  Keep the real stdout aside and point fd 1 at stderr for the run.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -670,7 +686,7 @@ def main():
         }
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
+        emit(json.dumps(line))
     barrier()
     if world > 1:
         dist.destroy_process_group()
