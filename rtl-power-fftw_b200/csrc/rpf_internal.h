@@ -84,7 +84,8 @@ cudaError_t rpf_launch_bluestein(const RpfBluestein &B, const uint8_t *bytes, in
 cudaError_t rpf_launch_fourstep_outer(int M, const uint8_t *bytes, int64_t nspec, const float2 *twiddle_big,
                                       const float *window, float2 *scratch, int sms, cudaStream_t stream);
 
-// The same pass as a TMA-staged streaming kernel (bulk loads -> shared-memory ring -> bulk stores): the product path.
+// The same pass as a TMA-staged streaming kernel (bulk loads -> shared-memory ring -> bulk stores): the outer pass of the
+// two-kernel path (launches of fewer than 96 spectra, RPF_FLAG_FOURSTEP).
 cudaError_t rpf_launch_fourstep_outer_tma(int M, const uint8_t *bytes, int64_t nspec, const float2 *twiddle_big,
                                           const float *window, float2 *scratch, int sms, cudaStream_t stream);
 cudaError_t rpf_outer_tma_configure();
