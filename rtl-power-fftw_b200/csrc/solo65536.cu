@@ -12,11 +12,12 @@
 //
 //   * the 256 values a thread hands to itself per spectrum go through a per-CTA scratch of 512 KiB in global memory
 //     (148 x 512 KiB = 74 MB: meant to stay in the 126 MB L2).  Thread t only ever touches [..][t]: no barrier, no
-//     fence, no flag on the compute warps' side beyond one mbarrier arrive per iteration.  Written with st.global (16
-//     per outer stage, 256 B per warp); read back by the three otherwise idle warps of the copy warp group with 16-byte
-//     cp.async (LDGSTS) into a 32 KiB row slot per stream, two to three stages before pass 1 needs the row (a first
-//     version loaded the rows with ld.global straight into the idle stream's registers: one stage of distance is less
-//     than the L2 latency under load, 10 % of all warp samples sat on the first use);
+//     fence, no flag on the compute warps' side beyond three mbarrier arrives per iteration.  Written with st.global (16
+//     per outer stage, 256 B per warp); read back by two otherwise idle warps of the copy warp group with 16-byte
+//     cp.async (LDGSTS) into a 32 KiB row slot per stream as soon as that slot has been read, a whole iteration before
+//     pass 1 needs the row -- only the first two rows of a spectrum also wait for its last outer stage (a first version
+//     loaded the rows with ld.global straight into the idle stream's registers: one stage of distance is less than the
+//     L2 latency under load, 10 % of all warp samples sat on the first use);
 //   * the scratch is reused IN PLACE: spectrum s lives as [ko][a] blocks of 2 KiB, spectrum s + 1 with the fields
 //     ko >> 1 and a >> (5 - log2 M) of the block index exchanged -- the outer stages of iteration i of the next spectrum
 //     (a >> (5 - log2 M) = i) overwrite exactly the rows ko = 2i, 2i + 1 of the current one, consumed an iteration
@@ -33,11 +34,11 @@
 // Iteration = two inner transforms (streams A: ko = 2i, B: ko = 2i + 1 of the same spectrum) + two outer stages of the
 // next spectrum, 8 iterations per spectrum, stage order (A,1)(B,1)(A,2)(B,2) O O (A,3)(B,3) as in cluster65536.cu; the
 // S1/S2 exchanges and their four split barriers are those of pipe4096.cu.  Raw bytes: 16 bulk copies of 1 KiB per
-// iteration (the 512 columns of both outer stages x 16 values of n1) into a four-deep ring with a full/empty mbarrier
+// iteration (the 512 columns of both outer stages x 16 values of n1) into a two-deep ring with a full/empty mbarrier
 // pair per slot.  With a window: byte - 127 (exact), the 16 window values of an outer stage come from global memory (L2)
 // and ride in the first radix-4 layer of the outer radix-16 (dft16_first_windowed), as in pipe4096.cu.
 //
-// Replaces reference src/datastore.cxx:68-87 for N = 65536.
+// Replaces reference src/datastore.cxx:68-87 for N = 8192 ... 65536 (launches of at least 96 spectra).
 #include <stdint.h>
 #include <type_traits>
 #include "fft_math.cuh"
