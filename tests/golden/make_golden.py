@@ -28,6 +28,9 @@ CASES = [
     ("n65536x3",      65536, 3,       False,  1638400 // 4, "gauss"),     # config 4 shape: straddling buffers
     ("n64x50_tone",   64,    50,      False,  16384,      "tone"),
     ("n2048x9",       2048,  9,       False,  16384,      "uniform"),
+    # one read of 120 spectra: the launch goes to the one-CTA-per-spectrum kernel (>= 96 spectra; hand-off through
+    # tensor memory at 8192 bins) -- appended last so that the seeds of the fixtures above do not move
+    ("n8192x120_one_read", 8192, 120, False,  2 * 8192 * 120, "gauss"),
 ]
 
 
