@@ -187,7 +187,8 @@ def test_text_output_matches_the_references_own_acquisition_layer(tmp_path, name
             assert ln in r.stderr, ln
 
 
-@pytest.mark.parametrize("N,flags", [(4096, 0), (4096, 1), (512, 0), (1024, 0), (2048, 0), (2048, 8), (512, 32), (1024, 32), (2048, 32), (65536, 0), (65536, 16), (65536, 128)])
+@pytest.mark.parametrize("N,flags", [(4096, 0), (4096, 1), (512, 0), (1024, 0), (2048, 0), (2048, 8), (512, 32), (1024, 32), (2048, 32), (65536, 0), (65536, 16), (65536, 128),
+                                     (8192, 0), (16384, 0), (32768, 0), (32768, 128)])
 def test_no_data_race_shows_as_nondeterminism(N, flags):
     """compute-sanitizer racecheck does not model the inline-PTX mbarrier arrive/wait pairs that order the S1/S2
     exchange buffers, so the evidence is empirical: a race would perturb some bin in some run.
